@@ -1,0 +1,218 @@
+// Fused softmax(Q K^T * scale) V for spatial-reduction attention (mix_transformer_evp.py:123-127) and the
+// flow cross-attention (nn.MultiheadAttention, mix_transformer_evp.py:868-883).  One CTA = 64 query rows of one
+// (frame, head); K/V are streamed through shared memory in 64-key tiles with an online softmax, so the
+// [B, heads, N, N_kv] attention matrix the reference materialises never exists.  bf16 operands, fp32 softmax and
+// accumulation.  Tensor-core path: mma.sync m16n8k16 (round-1 implementation; 2.6 % of the path's FLOPs).
+#include "kernels.cuh"
+
+namespace sv {
+
+namespace {
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kTile = 64;  // query rows per CTA and keys per smem tile
+
+template <int HD>
+struct AttnShape {
+  static constexpr int HDP = (HD + 15) / 16 * 16;  // head dim padded to the MMA K granularity
+  static constexpr int KS = HDP / 16;              // k-steps of Q K^T
+  static constexpr int NTO = HDP / 8;              // n-tiles of the output
+  static constexpr int LDS = HDP + 8;              // smem row stride (elements): odd multiple of 16 B -> conflict-free ldmatrix
+};
+
+// rows [r0, r0+64) x HD columns of a bf16 matrix -> smem tile [64][LDS], zero-filling OOB rows and pad columns
+template <int HD>
+__device__ __forceinline__ void load_tile(bf16* __restrict__ dst, const bf16* __restrict__ src, int64_t ld, int r0, int rows_total) {
+  using S = AttnShape<HD>;
+  constexpr int CH = S::HDP / 8;
+  for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+    const int r = i / CH, c = i % CH;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < rows_total && c * 8 < HD) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r0 + r) * ld + c * 8));
+    *reinterpret_cast<uint4*>(dst + r * S::LDS + c * 8) = v;
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
+                                                        const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
+                                                        int Nq, int Nkv, float scale_log2) {
+  using S = AttnShape<HD>;
+  __shared__ __align__(16) bf16 Qs[kTile * S::LDS];
+  __shared__ __align__(16) bf16 Ks[kTile * S::LDS];
+  __shared__ __align__(16) bf16 Vs[kTile * S::LDS];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * kTile;
+  const bf16* qb = q + static_cast<int64_t>(b) * Nq * ldq + head * HD;
+  const bf16* kb = k + static_cast<int64_t>(b) * Nkv * ldk + head * HD;
+  const bf16* vb = v + static_cast<int64_t>(b) * Nkv * ldv + head * HD;
+  bf16* ob = o + static_cast<int64_t>(b) * Nq * ldo + head * HD;
+
+  load_tile<HD>(Qs, qb, ldq, q0, Nq);
+  __syncthreads();
+
+  // Q fragments of this warp's 16 rows stay in registers for the whole kernel
+  uint32_t qf[S::KS][4];
+  {
+    const int mi = lane >> 3;
+    const int row = warp * 16 + (mi & 1) * 8 + (lane & 7);
+#pragma unroll
+    for (int ks = 0; ks < S::KS; ++ks) {
+      const int col = ks * 16 + (mi >> 1) * 8;
+      ldmatrix_x4(qf[ks], static_cast<uint32_t>(__cvta_generic_to_shared(Qs + row * S::LDS + col)));
+    }
+  }
+
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  float oacc[S::NTO][4];
+#pragma unroll
+  for (int i = 0; i < S::NTO; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f; }
+
+  for (int kv0 = 0; kv0 < Nkv; kv0 += kTile) {
+    __syncthreads();  // previous tile fully consumed
+    load_tile<HD>(Ks, kb, ldk, kv0, Nkv);
+    load_tile<HD>(Vs, vb, ldv, kv0, Nkv);
+    __syncthreads();
+
+    // S = Q K^T for 64 keys: 8 n-tiles
+    float sacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f; }
+    {
+      const int mi = lane >> 3;
+#pragma unroll
+      for (int ks = 0; ks < S::KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {  // pairs of key n-tiles
+          const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
+          const int col = ks * 16 + (mi & 1) * 8;
+          uint32_t kf[4];
+          ldmatrix_x4(kf, static_cast<uint32_t>(__cvta_generic_to_shared(Ks + key * S::LDS + col)));
+          mma_bf16_16816(sacc[np * 2], qf[ks], kf[0], kf[1]);
+          mma_bf16_16816(sacc[np * 2 + 1], qf[ks], kf[2], kf[3]);
+        }
+      }
+    }
+    // scale (log2 domain), mask keys beyond Nkv, online softmax
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = kv0 + nt * 8 + t * 2 + (e & 1);
+        float s = sacc[nt][e] * scale_log2;
+        if (key >= Nkv) s = -INFINITY;
+        sacc[nt][e] = s;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s);
+      }
+    }
+    float corr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every tile has >= 1 valid key
+      corr[r] = exp2f(m_run[r] - m_new);
+      m_run[r] = m_new;
+      l_run[r] *= corr[r];
+    }
+#pragma unroll
+    for (int i = 0; i < S::NTO; ++i) {
+      oacc[i][0] *= corr[0]; oacc[i][1] *= corr[0];
+      oacc[i][2] *= corr[1]; oacc[i][3] *= corr[1];
+    }
+    uint32_t pf[4][4];  // P as A-fragments for the 4 key k-steps
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(sacc[nt][0] - m_run[0]);
+      const float p1 = exp2f(sacc[nt][1] - m_run[0]);
+      const float p2 = exp2f(sacc[nt][2] - m_run[1]);
+      const float p3 = exp2f(sacc[nt][3] - m_run[1]);
+      l_run[0] += p0 + p1;
+      l_run[1] += p2 + p3;
+      const int kk = nt >> 1;
+      if ((nt & 1) == 0) { pf[kk][0] = pack_bf16x2(p0, p1); pf[kk][1] = pack_bf16x2(p2, p3); }
+      else               { pf[kk][2] = pack_bf16x2(p0, p1); pf[kk][3] = pack_bf16x2(p2, p3); }
+    }
+    // O += P V
+    {
+      const int mi = lane >> 3;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < S::NTO / 2; ++dp) {
+          const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+          const int col = (dp * 2 + (mi >> 1)) * 8;
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, static_cast<uint32_t>(__cvta_generic_to_shared(Vs + key * S::LDS + col)));
+          mma_bf16_16816(oacc[dp * 2], pf[kk], vf[0], vf[1]);
+          mma_bf16_16816(oacc[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+  const int row0 = q0 + warp * 16 + g, row1 = row0 + 8;
+#pragma unroll
+  for (int i = 0; i < S::NTO; ++i) {
+    const int col = i * 8 + t * 2;
+    if (col < HD) {
+      if (row0 < Nq) *reinterpret_cast<uint32_t*>(ob + static_cast<int64_t>(row0) * ldo + col) = pack_bf16x2(oacc[i][0] * inv0, oacc[i][1] * inv0);
+      if (row1 < Nq) *reinterpret_cast<uint32_t*>(ob + static_cast<int64_t>(row1) * ldo + col) = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
+    }
+  }
+}
+
+template <int HD>
+int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads,
+                int Nq, int Nkv, float scale, cudaStream_t st) {
+  dim3 grid(ceil_div(Nq, kTile), heads, B);
+  attention_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale * 1.4426950408889634f);
+  return launch_status("attention_kernel");
+}
+
+}  // namespace
+
+int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B,
+                     int heads, int Nq, int Nkv, int hd, float scale, cudaStream_t st) {
+  SV_CHECK(B > 0 && heads > 0 && Nq > 0 && Nkv > 0, "attention dims");
+  SV_CHECK(B <= 65535 && heads <= 65535, "attention grid limits");
+  SV_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention leading dims must keep 16-byte row alignment");
+  SV_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0, "attention operand alignment");
+  switch (hd) {
+    case 32: return attn_launch<32>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
+    case 40: return attn_launch<40>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
+    case 64: return attn_launch<64>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
+    default: return fail(SV_ERR_UNSUPPORTED, "attention head_dim must be 32, 40 or 64");
+  }
+}
+
+}  // namespace sv
+
+extern "C" int sv_op_attention(const uint16_t* q, int64_t ldq, const uint16_t* k, int64_t ldk, const uint16_t* v, int64_t ldv, uint16_t* o,
+                               int64_t ldo, int32_t B, int32_t heads, int32_t Nq, int32_t Nkv, int32_t hd, float scale, void* stream) {
+  return sv::launch_attention(reinterpret_cast<const sv::bf16*>(q), ldq, reinterpret_cast<const sv::bf16*>(k), ldk,
+                              reinterpret_cast<const sv::bf16*>(v), ldv, reinterpret_cast<sv::bf16*>(o), ldo, B, heads, Nq, Nkv, hd, scale,
+                              static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,419 @@
+// HBM-bound kernels of the LFB path: LayerNorm, patch gather (im2col), depthwise 3x3 + GELU, Gaussian 5x5,
+// bilinear token resize, token mean.  All 128-bit vectorised on channels-last (token-major == NHWC) tensors;
+// the reference's NCHW<->NLC transposes (mix_transformer_evp.py:26-28, 115-116, 212, 376) never happen.
+#include "kernels.cuh"
+
+namespace sv {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ LayerNorm
+// LPR lanes cooperate on one row (32/LPR rows per warp); each lane holds NV float4 of the row in registers.
+// Two-pass (mean, then centred variance) like ATen's CPU/CUDA LayerNorm; biased variance; eps inside sqrt.
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int64_t rows, int C,
+                                                         float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const int64_t warp_global = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t row = warp_global * RPW + lane / LPR;
+  const bool row_ok = row < rows;
+  const int nvec = C >> 2;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sub + i * LPR;
+    if (row_ok && vi < nvec) {
+      v[i] = *reinterpret_cast<const float4*>(x + row * C + vi * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sub + i * LPR;
+    if (vi < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
+  if (!row_ok) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = sub + i * LPR;
+    if (vi < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + vi * 4));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + vi * 4));
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + vi * 4) = y;
+      if (out_bf16) {
+        uint2 o;
+        o.x = pack_bf16x2(y.x, y.y);
+        o.y = pack_bf16x2(y.z, y.w);
+        *reinterpret_cast<uint2*>(out_bf16 + row * C + vi * 4) = o;
+      }
+    }
+  }
+}
+
+template <int LPR, int NV>
+int ln_launch(const float* x, const float* g, const float* b, float eps, int64_t rows, int C, float* of, bf16* ob, cudaStream_t st) {
+  constexpr int RPW = 32 / LPR;
+  const int64_t warps = ceil_div64(rows, RPW);
+  const int64_t blocks = ceil_div64(warps, 8);
+  layernorm_kernel<LPR, NV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, rows, C, of, ob);
+  return launch_status("layernorm_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ im2col
+// NHWC bf16 source, Cin % 8 == 0: one thread moves one 16-byte channel chunk of one (m, kh, kw) tap.
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ src, int B, int Cin, int H, int W, int k, int stride,
+                                                          int pad, int Ho, int Wo, bf16* __restrict__ out, int64_t ldo) {
+  const int cv = Cin >> 3;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * k * k * cv;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cv);
+  int64_t t = idx / cv;
+  const int kw = static_cast<int>(t % k); t /= k;
+  const int kh = static_cast<int>(t % k); t /= k;
+  const int64_t m = t;
+  const int ow = static_cast<int>(m % Wo);
+  const int oh = static_cast<int>((m / Wo) % Ho);
+  const int b = static_cast<int>(m / (static_cast<int64_t>(Wo) * Ho));
+  const int ih = oh * stride - pad + kh;
+  const int iw = ow * stride - pad + kw;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+    v = __ldg(reinterpret_cast<const uint4*>(src + ((static_cast<int64_t>(b) * H + ih) * W + iw) * Cin + c8 * 8));
+  *reinterpret_cast<uint4*>(out + m * ldo + (kh * k + kw) * Cin + c8 * 8) = v;
+}
+
+// NCHW fp32 source (network inputs: Cin = 3 or 2): one thread gathers 8 consecutive k indices (kh,kw,c order).
+__global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ src, int B, int Cin, int H, int W, int k, int stride,
+                                                              int pad, int Ho, int Wo, bf16* __restrict__ out, int64_t ldo) {
+  const int K = k * k * Cin;
+  const int kchunks = static_cast<int>(ldo >> 3);
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * kchunks;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kc = static_cast<int>(idx % kchunks);
+  const int64_t m = idx / kchunks;
+  const int ow = static_cast<int>(m % Wo);
+  const int oh = static_cast<int>((m / Wo) % Ho);
+  const int b = static_cast<int>(m / (static_cast<int64_t>(Wo) * Ho));
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kk = kc * 8 + j;
+    float val = 0.f;
+    if (kk < K) {
+      const int c = kk % Cin;
+      const int kw = (kk / Cin) % k;
+      const int kh = kk / (Cin * k);
+      const int ih = oh * stride - pad + kh;
+      const int iw = ow * stride - pad + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(src + ((static_cast<int64_t>(b) * Cin + c) * H + ih) * W + iw);
+    }
+    f[j] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(f[0], f[1]);
+  o.y = pack_bf16x2(f[2], f[3]);
+  o.z = pack_bf16x2(f[4], f[5]);
+  o.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(out + m * ldo + kc * 8) = o;
+}
+
+// ------------------------------------------------------------------------------------------ DWConv3x3 + bias + GELU
+// NHWC bf16; one thread owns 8 channels of a vertical run of R output pixels and slides a 3x3 window down the
+// column, so each input row segment is loaded once per thread and the 72 weights stay in registers.
+constexpr int kDwRun = 7;
+
+__device__ __forceinline__ void dw_load_row(const bf16* __restrict__ base, int hh, int w, int H, int W, int C, uint4 (&row)[3]) {
+#pragma unroll
+  for (int dx = 0; dx < 3; ++dx) {
+    const int ww = w + dx - 1;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      row[dx] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(hh) * W + ww) * C));
+    else
+      row[dx] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4& x, const float (&w)[8]) {
+  const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
+  acc[0] = fmaf(a.x, w[0], acc[0]); acc[1] = fmaf(a.y, w[1], acc[1]);
+  acc[2] = fmaf(b.x, w[2], acc[2]); acc[3] = fmaf(b.y, w[3], acc[3]);
+  acc[4] = fmaf(c.x, w[4], acc[4]); acc[5] = fmaf(c.y, w[5], acc[5]);
+  acc[6] = fmaf(d.x, w[6], acc[6]); acc[7] = fmaf(d.y, w[7], acc[7]);
+}
+
+__global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
+                                                             const float* __restrict__ bias, int B, int H, int W, int C,
+                                                             bf16* __restrict__ out) {
+  const int cv = C >> 3;
+  const int hsegs = (H + kDwRun - 1) / kDwRun;
+  const int64_t total = static_cast<int64_t>(B) * hsegs * W * cv;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cv);
+  int64_t t = idx / cv;
+  const int w = static_cast<int>(t % W); t /= W;
+  const int hs = static_cast<int>(t % hsegs);
+  const int b = static_cast<int>(t / hsegs);
+  const int c0 = c8 * 8;
+
+  float wt[9][8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0 + 4));
+    wt[tap][0] = a.x; wt[tap][1] = a.y; wt[tap][2] = a.z; wt[tap][3] = a.w;
+    wt[tap][4] = bq.x; wt[tap][5] = bq.y; wt[tap][6] = bq.z; wt[tap][7] = bq.w;
+  }
+  float bs[8];
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w; bs[4] = bq.x; bs[5] = bq.y; bs[6] = bq.z; bs[7] = bq.w;
+  }
+  const bf16* base = x + static_cast<int64_t>(b) * H * W * C + c0;
+  bf16* obase = out + static_cast<int64_t>(b) * H * W * C + c0;
+  const int h0 = hs * kDwRun;
+  const int h1 = min(h0 + kDwRun, H);
+  uint4 prev[3], cur[3], next[3];
+  dw_load_row(base, h0 - 1, w, H, W, C, prev);
+  dw_load_row(base, h0, w, H, W, C, cur);
+  for (int h = h0; h < h1; ++h) {
+    dw_load_row(base, h + 1, w, H, W, C, next);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      dw_fma8(acc, prev[dx], wt[0 * 3 + dx]);
+      dw_fma8(acc, cur[dx], wt[1 * 3 + dx]);
+      dw_fma8(acc, next[dx], wt[2 * 3 + dx]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(gelu_erf(acc[0]), gelu_erf(acc[1]));
+    o.y = pack_bf16x2(gelu_erf(acc[2]), gelu_erf(acc[3]));
+    o.z = pack_bf16x2(gelu_erf(acc[4]), gelu_erf(acc[5]));
+    o.w = pack_bf16x2(gelu_erf(acc[6]), gelu_erf(acc[7]));
+    *reinterpret_cast<uint4*>(obase + (static_cast<int64_t>(h) * W + w) * C) = o;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) { prev[dx] = cur[dx]; cur[dx] = next[dx]; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ Gaussian 5x5 (reflect pad 2)
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int H, int W) {
+  const int64_t total = static_cast<int64_t>(planes) * H * W;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = static_cast<int>(idx % W);
+  const int h = static_cast<int>((idx / W) % H);
+  const int64_t pl = idx / (static_cast<int64_t>(W) * H);
+  const float* src = x + pl * H * W;
+  const float k1[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
+  float acc = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    const int hh = reflect_idx(h + dy - 2, H);
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) {
+      const int ww = reflect_idx(w + dx - 2, W);
+      acc = fmaf(__ldg(src + static_cast<int64_t>(hh) * W + ww), k1[dy] * k1[dx] * (1.0f / 256.0f), acc);
+    }
+  }
+  out[idx] = acc;
+}
+
+// ------------------------------------------------------------------------------------------ bilinear resize (align_corners=False)
+__device__ __forceinline__ void bilinear_src(int dst, int in, int outn, int& i0, int& i1, float& l1) {
+  const float scale = static_cast<float>(in) / static_cast<float>(outn);
+  float s = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = static_cast<int>(s);
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = s - static_cast<float>(i0);
+}
+
+__global__ void __launch_bounds__(256) bilinear_tokens_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
+                                                              bf16* __restrict__ out, int64_t ldo) {
+  const int cv = C >> 3;
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * cv;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % cv);
+  const int64_t m = idx / cv;
+  const int ow = static_cast<int>(m % Wo);
+  const int oh = static_cast<int>((m / Wo) % Ho);
+  const int b = static_cast<int>(m / (static_cast<int64_t>(Wo) * Ho));
+  int h0, h1, w0, w1;
+  float lh, lw;
+  bilinear_src(oh, H, Ho, h0, h1, lh);
+  bilinear_src(ow, W, Wo, w0, w1, lw);
+  const bf16* base = x + static_cast<int64_t>(b) * H * W * C + c8 * 8;
+  const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(h0) * W + w0) * C));
+  const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(h0) * W + w1) * C));
+  const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(h1) * W + w0) * C));
+  const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(h1) * W + w1) * C));
+  const float w00 = (1.f - lh) * (1.f - lw), w01 = (1.f - lh) * lw, w10 = lh * (1.f - lw), w11 = lh * lw;
+  const uint32_t* p00 = &v00.x; const uint32_t* p01 = &v01.x; const uint32_t* p10 = &v10.x; const uint32_t* p11 = &v11.x;
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = unpack_bf16x2(p00[j]), bq = unpack_bf16x2(p01[j]), c = unpack_bf16x2(p10[j]), d = unpack_bf16x2(p11[j]);
+    o[j] = pack_bf16x2(w00 * a.x + w01 * bq.x + w10 * c.x + w11 * d.x, w00 * a.y + w01 * bq.y + w10 * c.y + w11 * d.y);
+  }
+  *reinterpret_cast<uint4*>(out + m * ldo + c8 * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------------------------------ misc
+__global__ void __launch_bounds__(256) token_mean_kernel(const float* __restrict__ x, int B, int tokens, int C, float* __restrict__ out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * C) return;
+  const int c = static_cast<int>(idx % C);
+  const int64_t b = idx / C;
+  const float* p = x + b * tokens * C + c;
+  float s = 0.f;
+  for (int t = 0; t < tokens; ++t) s += p[static_cast<int64_t>(t) * C];
+  out[idx] = s / static_cast<float>(tokens);
+}
+
+__global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict__ out, int64_t n) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = __bfloat162float(x[idx]);
+}
+
+__global__ void __launch_bounds__(256) copy_bf16_strided_kernel(const bf16* __restrict__ x, int64_t rows, int C, bf16* __restrict__ out, int64_t ldo) {
+  const int cv = C >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * cv) return;
+  const int c8 = static_cast<int>(idx % cv);
+  const int64_t r = idx / cv;
+  *reinterpret_cast<uint4*>(out + r * ldo + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(x + r * C + c8 * 8));
+}
+
+inline unsigned blocks_for(int64_t total) { return static_cast<unsigned>(ceil_div64(total, 256)); }
+
+}  // namespace
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                     bf16* out_bf16, cudaStream_t st) {
+  SV_CHECK(C % 4 == 0 && C >= 4 && C <= 512, "layernorm supports C%4==0, C<=512");
+  SV_CHECK(rows > 0, "layernorm rows");
+  const int nvec = C / 4;
+  if (nvec <= 4) return ln_launch<4, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  if (nvec <= 8) return ln_launch<8, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  if (nvec <= 16) return ln_launch<16, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  if (nvec <= 32) return ln_launch<32, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  if (nvec <= 64) return ln_launch<32, 2>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  if (nvec <= 96) return ln_launch<32, 3>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+  return ln_launch<32, 4>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+}
+
+int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, int Cin, int H, int W, int k, int stride, int pad,
+                  bf16* out, int64_t ldo, cudaStream_t st) {
+  const int Ho = conv_out_dim(H, k, stride, pad), Wo = conv_out_dim(W, k, stride, pad);
+  SV_CHECK(Ho > 0 && Wo > 0, "im2col output empty");
+  const int K = k * k * Cin;
+  SV_CHECK(ldo % 8 == 0 && ldo >= K, "im2col ldo must be a multiple of 8 and >= k*k*Cin");
+  if (src_nchw_f32 != nullptr) {
+    const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (ldo / 8);
+    im2col_nchw_f32_kernel<<<blocks_for(total), 256, 0, st>>>(src_nchw_f32, B, Cin, H, W, k, stride, pad, Ho, Wo, out, ldo);
+    return launch_status("im2col_nchw_f32_kernel");
+  }
+  SV_CHECK(src_nhwc_bf16 != nullptr, "im2col needs a source");
+  SV_CHECK(Cin % 8 == 0 && ldo == K, "im2col NHWC path needs Cin%8==0 and ldo==k*k*Cin");
+  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * k * k * (Cin / 8);
+  im2col_nhwc_kernel<<<blocks_for(total), 256, 0, st>>>(src_nhwc_bf16, B, Cin, H, W, k, stride, pad, Ho, Wo, out, ldo);
+  return launch_status("im2col_nhwc_kernel");
+}
+
+int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st) {
+  SV_CHECK(C % 8 == 0, "dwconv needs C%8==0");
+  const int64_t total = static_cast<int64_t>(B) * ceil_div(H, kDwRun) * W * (C / 8);
+  dwconv3x3_gelu_kernel<<<blocks_for(total), 256, 0, st>>>(x, w9c, bias, B, H, W, C, out);
+  return launch_status("dwconv3x3_gelu_kernel");
+}
+
+int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st) {
+  SV_CHECK(H >= 3 && W >= 3, "gauss5x5 needs H,W >= 3 (reflect pad 2)");
+  gauss5x5_kernel<<<blocks_for(static_cast<int64_t>(planes) * H * W), 256, 0, st>>>(x, out, planes, H, W);
+  return launch_status("gauss5x5_kernel");
+}
+
+int launch_bilinear_tokens(const bf16* x, int B, int H, int W, int C, int Ho, int Wo, bf16* out, int64_t ldo, cudaStream_t st) {
+  SV_CHECK(C % 8 == 0 && ldo % 8 == 0 && ldo >= C, "bilinear needs C%8==0, ldo%8==0");
+  bilinear_tokens_kernel<<<blocks_for(static_cast<int64_t>(B) * Ho * Wo * (C / 8)), 256, 0, st>>>(x, B, H, W, C, Ho, Wo, out, ldo);
+  return launch_status("bilinear_tokens_kernel");
+}
+
+int launch_token_mean(const float* x, int B, int tokens, int C, float* out, cudaStream_t st) {
+  token_mean_kernel<<<blocks_for(static_cast<int64_t>(B) * C), 256, 0, st>>>(x, B, tokens, C, out);
+  return launch_status("token_mean_kernel");
+}
+
+int launch_bf16_to_f32(const bf16* x, float* out, int64_t n, cudaStream_t st) {
+  bf16_to_f32_kernel<<<blocks_for(n), 256, 0, st>>>(x, out, n);
+  return launch_status("bf16_to_f32_kernel");
+}
+
+int launch_copy_bf16_strided(const bf16* x, int64_t rows, int C, bf16* out, int64_t ldo, cudaStream_t st) {
+  SV_CHECK(C % 8 == 0 && ldo % 8 == 0, "strided copy needs C%8==0");
+  copy_bf16_strided_kernel<<<blocks_for(rows * (C / 8)), 256, 0, st>>>(x, rows, C, out, ldo);
+  return launch_status("copy_bf16_strided_kernel");
+}
+
+}  // namespace sv
+
+extern "C" {
+
+int sv_op_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int32_t C, float* out_f32,
+                    uint16_t* out_bf16, void* stream) {
+  return sv::launch_layernorm(x, gamma, beta, eps, rows, C, out_f32, reinterpret_cast<sv::bf16*>(out_bf16), static_cast<cudaStream_t>(stream));
+}
+int sv_op_im2col(const float* src_nchw_f32, const uint16_t* src_nhwc_bf16, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t k,
+                 int32_t stride, int32_t pad, uint16_t* out, int64_t ldo, void* stream) {
+  return sv::launch_im2col(src_nchw_f32, reinterpret_cast<const sv::bf16*>(src_nhwc_bf16), B, Cin, H, W, k, stride, pad,
+                           reinterpret_cast<sv::bf16*>(out), ldo, static_cast<cudaStream_t>(stream));
+}
+int sv_op_dwconv3x3_gelu(const uint16_t* x, const float* w, const float* bias, int32_t B, int32_t H, int32_t W, int32_t C, uint16_t* out,
+                         void* stream) {
+  return sv::launch_dwconv3x3_gelu(reinterpret_cast<const sv::bf16*>(x), w, bias, B, H, W, C, reinterpret_cast<sv::bf16*>(out),
+                                   static_cast<cudaStream_t>(stream));
+}
+int sv_op_gauss5x5(const float* x, float* out, int32_t planes, int32_t H, int32_t W, void* stream) {
+  return sv::launch_gauss5x5(x, out, planes, H, W, static_cast<cudaStream_t>(stream));
+}
+int sv_op_bilinear_tokens(const uint16_t* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Ho, int32_t Wo, uint16_t* out,
+                          int64_t ldo, void* stream) {
+  return sv::launch_bilinear_tokens(reinterpret_cast<const sv::bf16*>(x), B, H, W, C, Ho, Wo, reinterpret_cast<sv::bf16*>(out), ldo,
+                                    static_cast<cudaStream_t>(stream));
+}
+int sv_op_token_mean(const float* x, int32_t B, int32_t tokens, int32_t C, float* out, void* stream) {
+  return sv::launch_token_mean(x, B, tokens, C, out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// Host-side interface of the tcgen05 GEMM (gemm_tcgen05.cu).
+#pragma once
+#include "common.cuh"
+
+namespace sv {
+
+// out[M,N] = act(A[M,K] * W[N,K]^T + bias[N]) (+ residual[M,N])
+struct GemmDesc {
+  const bf16* A = nullptr;   // [M, K] row-major, row stride lda (elements)
+  int64_t lda = 0;
+  const bf16* W = nullptr;   // [N, K] row-major (nn.Linear weight layout), row stride ldw
+  int64_t ldw = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;      // [N] or null
+  int act = ACT_NONE;
+  const float* residual = nullptr;  // [M, N] fp32, row stride ldr, or null (may alias out if out_fp32)
+  int64_t ldr = 0;
+  void* out = nullptr;              // bf16 or fp32, row stride ldc
+  int64_t ldc = 0;
+  int out_fp32 = 0;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int block_n;      // UMMA N (multiple of 16, <= 256)
+  int num_stages;   // smem ring depth
+  int num_n_tiles;
+  int num_tiles;
+  int act;
+  int out_fp32;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  void* out;
+  long long ldc;
+};
+
+struct GemmPlan {
+  CUtensorMap tmap_a;
+  CUtensorMap tmap_w;
+  GemmParams p;
+  int grid = 0;
+  size_t smem_bytes = 0;
+  double flops = 0.0;
+};
+
+int gemm_plan(const GemmDesc& d, GemmPlan* plan);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+// pick the UMMA N for a problem (exposed for tests)
+int gemm_pick_block_n(int M, int N, int K, int num_sms);
+
+}  // namespace sv

@@ -1,0 +1,22 @@
+// Launchers of the HBM-bound (non-GEMM) kernels; defined in elementwise.cu / attention.cu.
+#pragma once
+#include "common.cuh"
+
+namespace sv {
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                     bf16* out_bf16, cudaStream_t st);
+int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, int Cin, int H, int W, int k, int stride, int pad,
+                  bf16* out, int64_t ldo, cudaStream_t st);
+int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st);
+int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st);
+int launch_bilinear_tokens(const bf16* x, int B, int H, int W, int C, int Ho, int Wo, bf16* out, int64_t ldo, cudaStream_t st);
+int launch_token_mean(const float* x, int B, int tokens, int C, float* out, cudaStream_t st);
+int launch_bf16_to_f32(const bf16* x, float* out, int64_t n, cudaStream_t st);
+int launch_copy_bf16_strided(const bf16* x, int64_t rows, int C, bf16* out, int64_t ldo, cudaStream_t st);
+int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B,
+                     int heads, int Nq, int Nkv, int hd, float scale, cudaStream_t st);
+
+inline int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+}  // namespace sv

@@ -1,0 +1,402 @@
+// MS-TCN MultiStageModel_S (mstcn.py:94-130, 153-178, 181-214) for sm_100a, fp32, all videos of a batch at once.
+//
+// Layout: activations are TIME-MAJOR [T_total, F] fp32 (the memory layout of the reference's `long_feature`,
+// trans_SV_output.py:271-272), videos concatenated; a per-frame "video start row" array masks causal history at
+// video boundaries, so one launch per layer covers every video.  The causal branch (mstcn_causal_conv=True) is
+//   y[t] = x[t] + W1 * relu(Wd[0] x[t-2d] + Wd[1] x[t-d] + Wd[2] x[t] + bd) + b1        (mstcn.py:208-214)
+// which equals conv(pad 2d) -> relu -> drop last 2d samples -> 1x1 -> add.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace sv {
+namespace {
+
+// ---- stage-1 input projection: out[t, f] = sum_d feats[t, d] * W[f, d] + b[f]   (conv_1x1, mstcn.py:174)
+// fp32 SIMT GEMM, CTA tile 64 x F, K-chunk 32.  HBM-bound in principle (8 KB read per frame, 16 FLOP/B).
+template <int F>
+__global__ void __launch_bounds__(256) mstcn_inproj_kernel(const float* __restrict__ feats, const float* __restrict__ Wt /*[D][F]*/,
+                                                           const float* __restrict__ bias, int64_t T, int D, float* __restrict__ out) {
+  constexpr int BM = 64, BK = 32;
+  constexpr int TN = 4;
+  constexpr int TM = BM * F / (256 * TN);  // F=32 -> 2, F=64 -> 4
+  constexpr int TX = F / TN;               // threads along f
+  __shared__ float As[BK][BM + 1];         // [k][row]
+  __shared__ __align__(16) float Ws[BK][F];  // [k][f]
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += BK) {
+    // A tile: 64 rows x 32 k  (512 float4, 2 per thread), coalesced along d
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int v = tid + i * 256;
+      const int r = v / (BK / 4), c4 = v % (BK / 4);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < T) a = __ldg(reinterpret_cast<const float4*>(feats + (row0 + r) * D + k0 + c4 * 4));
+      As[c4 * 4 + 0][r] = a.x; As[c4 * 4 + 1][r] = a.y; As[c4 * 4 + 2][r] = a.z; As[c4 * 4 + 3][r] = a.w;
+    }
+    // W tile: 32 k x F
+    for (int v = tid; v < BK * F / 4; v += 256) {
+      const int kk = v / (F / 4), f4 = v % (F / 4);
+      *reinterpret_cast<float4*>(&Ws[kk][f4 * 4]) = __ldg(reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(k0 + kk) * F + f4 * 4));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][tx * TN]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float a = As[kk][ty * TM + i];
+        acc[i][0] = fmaf(a, w.x, acc[i][0]); acc[i][1] = fmaf(a, w.y, acc[i][1]);
+        acc[i][2] = fmaf(a, w.z, acc[i][2]); acc[i][3] = fmaf(a, w.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + tx * TN));
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t r = row0 + ty * TM + i;
+    if (r < T) *reinterpret_cast<float4*>(out + r * F + tx * TN) = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
+  }
+}
+
+// ---- one DilatedResidualLayer for every frame of every video. One thread = one time step, all F channels.
+// smem: Wd [3][F_in][F_out], W1 [F_in][F_out], bd[F], b1[F] (weights broadcast-read, conflict-free).
+template <int F>
+__global__ void __launch_bounds__(128) mstcn_layer_kernel(const float* __restrict__ x, const int* __restrict__ frame_start,
+                                                          const float* __restrict__ wpack, int dilation, int64_t T, float* __restrict__ y) {
+  extern __shared__ __align__(16) float sw[];
+  constexpr int NW = 3 * F * F + F * F + 2 * F;
+  for (int i = threadIdx.x; i < NW / 4; i += blockDim.x) reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(wpack) + i);
+  __syncthreads();
+  const float* Wd = sw;
+  const float* W1 = sw + 3 * F * F;
+  const float* bd = W1 + F * F;
+  const float* b1 = bd + F;
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int64_t start = frame_start[t];
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = bd[f];
+  float xt[F];  // x[t], kept for the residual
+#pragma unroll
+  for (int tap = 0; tap < 3; ++tap) {
+    const int64_t ts = t - static_cast<int64_t>(2 - tap) * dilation;
+    if (ts < start) continue;  // zero left padding (and never read across a video boundary)
+    const float4* xp = reinterpret_cast<const float4*>(x + ts * F);
+#pragma unroll
+    for (int c4 = 0; c4 < F / 4; ++c4) {
+      const float4 xv = __ldg(xp + c4);
+      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (tap == 2) { xt[c4 * 4] = xv.x; xt[c4 * 4 + 1] = xv.y; xt[c4 * 4 + 2] = xv.z; xt[c4 * 4 + 3] = xv.w; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(Wd + (tap * F + c4 * 4 + j) * F);
+#pragma unroll
+        for (int f4 = 0; f4 < F / 4; ++f4) {
+          const float4 w = wr[f4];
+          acc[f4 * 4 + 0] = fmaf(xs[j], w.x, acc[f4 * 4 + 0]);
+          acc[f4 * 4 + 1] = fmaf(xs[j], w.y, acc[f4 * 4 + 1]);
+          acc[f4 * 4 + 2] = fmaf(xs[j], w.z, acc[f4 * 4 + 2]);
+          acc[f4 * 4 + 3] = fmaf(xs[j], w.w, acc[f4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  float out[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) out[f] = xt[f] + b1[f];
+#pragma unroll
+  for (int c = 0; c < F; ++c) {
+    const float h = fmaxf(acc[c], 0.f);
+    const float4* wr = reinterpret_cast<const float4*>(W1 + c * F);
+#pragma unroll
+    for (int f4 = 0; f4 < F / 4; ++f4) {
+      const float4 w = wr[f4];
+      out[f4 * 4 + 0] = fmaf(h, w.x, out[f4 * 4 + 0]);
+      out[f4 * 4 + 1] = fmaf(h, w.y, out[f4 * 4 + 1]);
+      out[f4 * 4 + 2] = fmaf(h, w.z, out[f4 * 4 + 2]);
+      out[f4 * 4 + 3] = fmaf(h, w.w, out[f4 * 4 + 3]);
+    }
+  }
+  float4* yp = reinterpret_cast<float4*>(y + t * F);
+#pragma unroll
+  for (int f4 = 0; f4 < F / 4; ++f4) yp[f4] = make_float4(out[f4 * 4], out[f4 * 4 + 1], out[f4 * 4 + 2], out[f4 * 4 + 3]);
+}
+
+// ---- conv_out_classes (mstcn.py:177): logits[c, t] = Wout[c,:] . h[t,:] + b[c]; channel-major output (coalesced over t).
+// Optionally fused with the next stage's softmax(dim=channels) + conv_1x1 (mstcn.py:126, 174): next[t, f].
+template <int F>
+__global__ void __launch_bounds__(128) mstcn_out_kernel(const float* __restrict__ h, const float* __restrict__ Wout /*[C][F]*/,
+                                                        const float* __restrict__ bout, int C, int64_t T, float* __restrict__ logits /*[C][T]*/,
+                                                        const float* __restrict__ Wnext /*[C][F] (k-major) or null*/,
+                                                        const float* __restrict__ bnext, float* __restrict__ next /*[T][F]*/) {
+  constexpr int MAXC = 32;
+  __shared__ float sWo[MAXC * F];
+  __shared__ float sWn[MAXC * F];
+  __shared__ float sbo[MAXC];
+  __shared__ float sbn[F];
+  for (int i = threadIdx.x; i < C * F; i += blockDim.x) { sWo[i] = Wout[i]; if (Wnext) sWn[i] = Wnext[i]; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sbo[i] = bout[i];
+  if (Wnext) for (int i = threadIdx.x; i < F; i += blockDim.x) sbn[i] = bnext[i];
+  __syncthreads();
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float hv[F];
+  const float4* hp = reinterpret_cast<const float4*>(h + t * F);
+#pragma unroll
+  for (int f4 = 0; f4 < F / 4; ++f4) { const float4 v = __ldg(hp + f4); hv[f4 * 4] = v.x; hv[f4 * 4 + 1] = v.y; hv[f4 * 4 + 2] = v.z; hv[f4 * 4 + 3] = v.w; }
+  float lg[MAXC];
+  float mx = -INFINITY;
+  for (int c = 0; c < C; ++c) {
+    float a = sbo[c];
+#pragma unroll
+    for (int f = 0; f < F; ++f) a = fmaf(hv[f], sWo[c * F + f], a);
+    lg[c] = a;
+    logits[static_cast<int64_t>(c) * T + t] = a;
+    mx = fmaxf(mx, a);
+  }
+  if (Wnext == nullptr) return;
+  float den = 0.f;
+  for (int c = 0; c < C; ++c) { lg[c] = expf(lg[c] - mx); den += lg[c]; }
+  const float inv = 1.0f / den;
+  float o[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) o[f] = sbn[f];
+  for (int c = 0; c < C; ++c) {
+    const float p = lg[c] * inv;
+#pragma unroll
+    for (int f = 0; f < F; ++f) o[f] = fmaf(p, sWn[c * F + f], o[f]);
+  }
+  float4* np = reinterpret_cast<float4*>(next + t * F);
+#pragma unroll
+  for (int f4 = 0; f4 < F / 4; ++f4) np[f4] = make_float4(o[f4 * 4], o[f4 * 4 + 1], o[f4 * 4 + 2], o[f4 * 4 + 3]);
+}
+
+__global__ void frame_start_kernel(const int64_t* __restrict__ offsets, int n_videos, int64_t T, int* __restrict__ frame_start) {
+  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  int lo = 0, hi = n_videos;  // find v with offsets[v] <= t < offsets[v+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (offsets[mid] <= t) lo = mid; else hi = mid;
+  }
+  frame_start[t] = static_cast<int>(offsets[lo]);
+}
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+}  // namespace
+}  // namespace sv
+
+struct sv_mstcn {
+  sv_mstcn_cfg cfg;
+  int device = 0;
+  std::map<std::string, sv::HostTensor> tensors;
+  bool packed = false;
+  float* d_weights = nullptr;  // single device blob
+  // offsets (in floats) into the blob
+  struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next; std::vector<size_t> layer; };
+  std::vector<Stage> stages;
+  int64_t launches = 0;
+};
+
+namespace sv {
+namespace {
+
+std::string stage_prefix(int s) { return s == 0 ? std::string("stage1_phase") : "stages." + std::to_string(s - 1); }
+
+int expect(const sv_mstcn* h, const std::string& key, std::initializer_list<int64_t> shape, const HostTensor** out) {
+  auto it = h->tensors.find(key);
+  if (it == h->tensors.end()) return fail(SV_ERR_STATE, "mstcn: missing state_dict key '" + key + "'");
+  if (it->second.shape != std::vector<int64_t>(shape)) return fail(SV_ERR_INVALID, "mstcn: wrong shape for '" + key + "'");
+  *out = &it->second;
+  return SV_OK;
+}
+
+template <int F>
+int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n_videos, int64_t T, float* logits, void* ws, cudaStream_t st) {
+  const sv_mstcn_cfg& c = h->cfg;
+  char* p = static_cast<char*>(ws);
+  float* bufA = reinterpret_cast<float*>(p);
+  float* bufB = bufA + T * F;
+  int* frame_start = reinterpret_cast<int*>(bufB + T * F);
+  const unsigned tb = static_cast<unsigned>(ceil_div64(T, 128));
+  frame_start_kernel<<<tb, 128, 0, st>>>(d_offsets, n_videos, T, frame_start);
+  SV_TRY(launch_status("frame_start_kernel"));
+  h->launches = 1;
+  const float* W = h->d_weights;
+  const size_t layer_smem = (3 * F * F + F * F + 2 * F) * sizeof(float);
+  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_layer_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(layer_smem)));
+  float* cur = bufA;  // current stage input / running activation
+  float* nxt = bufB;
+  for (int s = 0; s < c.stages; ++s) {
+    const sv_mstcn::Stage& S = h->stages[s];
+    if (s == 0) {
+      mstcn_inproj_kernel<F><<<static_cast<unsigned>(ceil_div64(T, 64)), 256, 0, st>>>(feats, W + S.w_in, W + S.b_in, T, c.f_dim, cur);
+      SV_TRY(launch_status("mstcn_inproj_kernel"));
+      ++h->launches;
+    }
+    for (int l = 0; l < c.layers; ++l) {
+      mstcn_layer_kernel<F><<<tb, 128, layer_smem, st>>>(cur, frame_start, W + S.layer[l], 1 << l, T, nxt);
+      SV_TRY(launch_status("mstcn_layer_kernel"));
+      ++h->launches;
+      std::swap(cur, nxt);
+    }
+    const bool last = s == c.stages - 1;
+    // writes this stage's logits; unless last, also softmax + the next stage's conv_1x1 into `nxt`
+    mstcn_out_kernel<F><<<tb, 128, 0, st>>>(cur, W + S.w_out, W + S.b_out, c.out_features, T, logits + static_cast<int64_t>(s) * c.out_features * T,
+                                           last ? nullptr : W + S.w_next, last ? nullptr : W + S.b_next, nxt);
+    SV_TRY(launch_status("mstcn_out_kernel"));
+    ++h->launches;
+    std::swap(cur, nxt);
+  }
+  return SV_OK;
+}
+
+}  // namespace
+}  // namespace sv
+
+extern "C" {
+
+int sv_mstcn_create(const sv_mstcn_cfg* cfg, sv_mstcn_handle** out) {
+  using namespace sv;
+  SV_CHECK(cfg && out, "null argument");
+  SV_CHECK(cfg->stages >= 1 && cfg->layers >= 1 && cfg->layers <= 16, "mstcn: stages>=1, 1<=layers<=16");
+  if (cfg->f_maps != 32 && cfg->f_maps != 64) return fail(SV_ERR_UNSUPPORTED, "mstcn: f_maps must be 32 or 64");
+  if (!cfg->causal) return fail(SV_ERR_UNSUPPORTED, "mstcn: only the causal branch (mstcn_causal_conv=True) is implemented");
+  SV_CHECK(cfg->out_features >= 1 && cfg->out_features <= 32, "mstcn: out_features in [1,32]");
+  SV_CHECK(cfg->f_dim % 32 == 0, "mstcn: f_dim must be a multiple of 32");
+  int dev = 0;
+  SV_CUDA_OK(cudaGetDevice(&dev));
+  sv_mstcn* h = new sv_mstcn();
+  h->cfg = *cfg;
+  h->device = dev;
+  *out = h;
+  return SV_OK;
+}
+
+int sv_mstcn_destroy(sv_mstcn_handle* h) {
+  if (!h) return SV_OK;
+  if (h->d_weights) cudaFree(h->d_weights);
+  delete h;
+  return SV_OK;
+}
+
+int sv_mstcn_set_tensor(sv_mstcn_handle* h, const char* name, const float* host_data, const int64_t* shape, int32_t ndim) {
+  using namespace sv;
+  SV_CHECK(h && name && host_data && (shape || ndim == 0), "null argument");
+  HostTensor t;
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= shape[i]; }
+  t.data.assign(host_data, host_data + n);
+  h->tensors[name] = std::move(t);
+  h->packed = false;
+  return SV_OK;
+}
+
+int sv_mstcn_pack_weights(sv_mstcn_handle* h) {
+  using namespace sv;
+  SV_CHECK(h, "null handle");
+  const sv_mstcn_cfg& c = h->cfg;
+  const int64_t F = c.f_maps, C = c.out_features;
+  std::vector<float> blob;
+  auto reserve = [&](size_t n) { size_t off = blob.size(); blob.resize(off + ((n + 3) / 4) * 4, 0.f); return off; };
+  h->stages.assign(c.stages, sv_mstcn::Stage());
+  for (int s = 0; s < c.stages; ++s) {
+    const std::string p = stage_prefix(s);
+    const int64_t dim = s == 0 ? c.f_dim : C;
+    sv_mstcn::Stage& S = h->stages[s];
+    const HostTensor *w, *b;
+    SV_TRY(expect(h, p + ".conv_1x1.weight", {F, dim, 1}, &w));
+    SV_TRY(expect(h, p + ".conv_1x1.bias", {F}, &b));
+    // k-major [dim][F] so that a K-chunk of W is contiguous over f
+    S.w_in = reserve(dim * F);
+    for (int64_t f = 0; f < F; ++f)
+      for (int64_t d = 0; d < dim; ++d) blob[S.w_in + d * F + f] = w->data[f * dim + d];
+    S.b_in = reserve(F);
+    std::copy(b->data.begin(), b->data.end(), blob.begin() + S.b_in);
+    for (int l = 0; l < c.layers; ++l) {
+      const std::string lp = p + ".layers." + std::to_string(l);
+      const HostTensor *wd, *bd, *w1, *b1;
+      SV_TRY(expect(h, lp + ".conv_dilated.weight", {F, F, 3}, &wd));
+      SV_TRY(expect(h, lp + ".conv_dilated.bias", {F}, &bd));
+      SV_TRY(expect(h, lp + ".conv_1x1.weight", {F, F, 1}, &w1));
+      SV_TRY(expect(h, lp + ".conv_1x1.bias", {F}, &b1));
+      const size_t off = reserve(3 * F * F + F * F + 2 * F);
+      S.layer.push_back(off);
+      // Wd[tap][cin][cout] ; conv1d weight is [cout][cin][tap], tap k multiplies x[t-(2-k)d]
+      for (int64_t k = 0; k < 3; ++k)
+        for (int64_t ci = 0; ci < F; ++ci)
+          for (int64_t co = 0; co < F; ++co) blob[off + (k * F + ci) * F + co] = wd->data[(co * F + ci) * 3 + k];
+      const size_t o1 = off + 3 * F * F;
+      for (int64_t ci = 0; ci < F; ++ci)
+        for (int64_t co = 0; co < F; ++co) blob[o1 + ci * F + co] = w1->data[co * F + ci];
+      std::copy(bd->data.begin(), bd->data.end(), blob.begin() + o1 + F * F);
+      std::copy(b1->data.begin(), b1->data.end(), blob.begin() + o1 + F * F + F);
+    }
+    SV_TRY(expect(h, p + ".conv_out_classes.weight", {C, F, 1}, &w));
+    SV_TRY(expect(h, p + ".conv_out_classes.bias", {C}, &b));
+    S.w_out = reserve(C * F);
+    std::copy(w->data.begin(), w->data.end(), blob.begin() + S.w_out);  // [C][F]
+    S.b_out = reserve(C);
+    std::copy(b->data.begin(), b->data.end(), blob.begin() + S.b_out);
+  }
+  // next-stage input projection in [C][F] (k-major) form next to the producing stage
+  for (int s = 0; s + 1 < c.stages; ++s) {
+    h->stages[s].w_next = h->stages[s + 1].w_in;
+    h->stages[s].b_next = h->stages[s + 1].b_in;
+  }
+  if (h->d_weights) { cudaFree(h->d_weights); h->d_weights = nullptr; }
+  SV_CUDA_OK(cudaSetDevice(h->device));
+  SV_CUDA_OK(cudaMalloc(&h->d_weights, blob.size() * sizeof(float)));
+  SV_CUDA_OK(cudaMemcpy(h->d_weights, blob.data(), blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->packed = true;
+  return SV_OK;
+}
+
+size_t sv_mstcn_workspace_bytes(const sv_mstcn_handle* h, int64_t total_frames) {
+  if (!h || total_frames <= 0) return 0;
+  const size_t T = static_cast<size_t>(total_frames);
+  return 2 * T * h->cfg.f_maps * sizeof(float) + T * sizeof(int) + 4096 * sizeof(int64_t) + 256;
+}
+
+int sv_mstcn_forward(sv_mstcn_handle* h, const float* feats, const int64_t* video_offsets, int32_t n_videos, float* logits,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace sv;
+  SV_CHECK(h && feats && video_offsets && logits && workspace, "null argument");
+  if (!h->packed) return fail(SV_ERR_STATE, "mstcn: pack_weights() has not been called");
+  SV_CHECK(n_videos >= 1 && n_videos < 4096, "mstcn: 1 <= n_videos < 4096");
+  SV_CHECK(video_offsets[0] == 0, "mstcn: video_offsets[0] must be 0");
+  for (int i = 0; i < n_videos; ++i) SV_CHECK(video_offsets[i + 1] > video_offsets[i], "mstcn: empty video / non-increasing offsets");
+  const int64_t T = video_offsets[n_videos];
+  SV_CHECK(T < (1LL << 31), "mstcn: too many frames");
+  SV_CHECK(workspace_bytes >= sv_mstcn_workspace_bytes(h, T), "mstcn: workspace too small");
+  SV_CHECK((reinterpret_cast<uintptr_t>(feats) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mstcn: alignment");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // offsets live at the tail of the workspace
+  char* tail = static_cast<char*>(workspace) + 2 * static_cast<size_t>(T) * h->cfg.f_maps * sizeof(float) + static_cast<size_t>(T) * sizeof(int);
+  tail = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tail) + 255) & ~static_cast<uintptr_t>(255));
+  int64_t* d_offsets = reinterpret_cast<int64_t*>(tail);
+  SV_CUDA_OK(cudaMemcpyAsync(d_offsets, video_offsets, (n_videos + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  if (h->cfg.f_maps == 32) return run_forward<32>(h, feats, d_offsets, n_videos, T, logits, workspace, st);
+  return run_forward<64>(h, feats, d_offsets, n_videos, T, logits, workspace, st);
+}
+
+int64_t sv_mstcn_last_launch_count(const sv_mstcn_handle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's LFB driver loop (generate_evp_LFB.py:439-499) and of the per-video MS-TCN
+call (trans_SV_output.py:250-301), plus the shard-by-video logic for multi-GPU runs.
+
+Frames and videos are independent, so N GPUs means N processes each extracting its own videos — there is no
+collective on the data path.  What the reference does per batch, and what happens here instead:
+  reference: `.to(device)` of pageable fp32 tensors, forward, `.cpu().numpy()`, `np.concatenate` (O(N^2) host copies,
+             float64 result because the seed array is float64, generate_evp_LFB.py:295-297,457);
+  here:      pinned host staging, H2D copies on a side stream overlapped with the previous batch's kernels, D2H of the
+             [B,2048] features into a preallocated pinned block; the float64 view is produced once at the end.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+def lpt_assign(lengths: Sequence[int], n_ranks: int) -> List[List[int]]:
+    """Longest-processing-time-first assignment of videos to ranks. Returns per-rank video indices, ascending."""
+    loads = [0] * n_ranks
+    buckets: List[List[int]] = [[] for _ in range(n_ranks)]
+    for v in sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i)):
+        r = min(range(n_ranks), key=lambda j: (loads[j], j))
+        buckets[r].append(v)
+        loads[r] += int(lengths[v])
+    return [sorted(b) for b in buckets]
+
+
+def gather_in_video_order(per_rank_blocks: Sequence[Sequence[np.ndarray]], assignment: Sequence[Sequence[int]], n_videos: int) -> np.ndarray:
+    """Host-side ordered gather: rank r produced one [T_v, D] block per video in `assignment[r]`; the LFB file is the
+    concatenation by video index (generate_evp_LFB.py:457; consumers slice by cumulative num_each, trans_SV_output.py:56-72)."""
+    slots: List[Optional[np.ndarray]] = [None] * n_videos
+    for blocks, vids in zip(per_rank_blocks, assignment):
+        if len(blocks) != len(vids):
+            raise ValueError("a rank returned a different number of blocks than it was assigned videos")
+        for blk, v in zip(blocks, vids):
+            slots[v] = blk
+    if any(s is None for s in slots):
+        raise ValueError("missing feature block for video(s) " + str([i for i, s in enumerate(slots) if s is None]))
+    return np.concatenate(slots, axis=0)
+
+
+class LFBExtractor:
+    """End-to-end feature extraction from HOST buffers through the drop-in model (the call a user of the reference
+    makes, with the reference's batch size of 200 by default: generate_evp_LFB.py:36 `--val`)."""
+
+    def __init__(self, model, batch_size: int = 200, device: Optional[torch.device] = None):
+        self.model = model
+        self.batch_size = int(batch_size)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._dev = None  # double-buffered device staging
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _staging(self, H, W, with_flow):
+        key = (H, W, with_flow)
+        if self._dev is None or self._dev[0] != key:
+            bufs = []
+            for _ in range(2):
+                x = torch.empty((self.batch_size, 3, H, W), dtype=torch.float32, device=self.device)
+                s = torch.empty((self.batch_size, 3, H, W), dtype=torch.float32, device=self.device)
+                f = torch.empty((self.batch_size, 2, H, W), dtype=torch.float32, device=self.device) if with_flow else None
+                bufs.append((x, s, f, torch.cuda.Event(), torch.cuda.Event()))
+            self._dev = (key, bufs)
+        return self._dev[1]
+
+    @torch.no_grad()
+    def extract(self, frames: torch.Tensor, segmaps: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """frames/segmaps: [N,(1,)3,H,W] fp32 HOST (pinned for full overlap), flow: [N,(1,)2,H,W] or None
+        -> [N, 2048] fp32 pinned host tensor (features in input order)."""
+        N = frames.shape[0]
+        H, W = frames.shape[-2], frames.shape[-1]
+        frames = frames.reshape(N, 3, H, W)
+        segmaps = segmaps.reshape(N, 3, H, W)
+        if flow is not None:
+            flow = flow.reshape(N, 2, H, W)
+        bufs = self._staging(H, W, flow is not None)
+        if out is None:
+            out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
+        compute = torch.cuda.current_stream(self.device)
+        self.h2d_bytes = self.d2h_bytes = 0
+        for bi, b0 in enumerate(range(0, N, self.batch_size)):
+            n = min(self.batch_size, N - b0)
+            x, s, f, ev_in, ev_free = bufs[bi % 2]
+            with torch.cuda.stream(self._copy_stream):
+                if bi >= 2:
+                    self._copy_stream.wait_event(ev_free)  # kernels that read this staging buffer have finished
+                x[:n].copy_(frames[b0:b0 + n], non_blocking=True)
+                s[:n].copy_(segmaps[b0:b0 + n], non_blocking=True)
+                self.h2d_bytes += 2 * n * 3 * H * W * 4
+                if f is not None:
+                    f[:n].copy_(flow[b0:b0 + n], non_blocking=True)
+                    self.h2d_bytes += n * 2 * H * W * 4
+                ev_in.record(self._copy_stream)
+            compute.wait_event(ev_in)
+            feats = self.model(x[:n], s[:n], None if f is None else f[:n], return_features=True)
+            ev_free.record(compute)
+            out[b0:b0 + n].copy_(feats, non_blocking=True)
+            self.d2h_bytes += n * self.model.embedding_dim * 4
+        compute.synchronize()
+        return out
+
+    def extract_float64(self, frames, segmaps, flow) -> np.ndarray:
+        """Same values as `extract`, as the float64 ndarray the reference pickles (generate_evp_LFB.py:513-520)."""
+        return self.extract(frames, segmaps, flow).numpy().astype(np.float64)
+
+
+@torch.no_grad()
+def run_mstcn_per_video(mstcn_model, lfb: torch.Tensor, lengths: Sequence[int]):
+    """The reference's per-video loop (trans_SV_output.py:250-301, MS-TCN part) done as ONE batched launch sequence:
+    returns the last stage's logits per video, each [out_features, T_v] (== model.forward(video_fe)[-1].squeeze(1)[0])."""
+    logits = mstcn_model.forward_videos(lfb, lengths)  # [stages, C, T_total]
+    outs, o = [], 0
+    for T in lengths:
+        outs.append(logits[-1, :, o:o + T])
+        o += T
+    return outs

@@ -1,0 +1,162 @@
+"""PyTorch custom ops (`torch.ops.surgvid.*`) over the C ABI, plus thin tensor wrappers of the single kernels.
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, workspace through the caching allocator)
+and the stream; all arithmetic happens inside libsurgvid.so.  CUDA only — there is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _native
+
+_HANDLES: Dict[int, "object"] = {}  # op-visible integer id -> owner object (keeps native handles alive)
+
+
+def _stream_ptr(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("surgvid ops run on CUDA tensors only (no CPU fallback); got a tensor on " + str(t.device))
+
+
+# ----------------------------------------------------------------------------------------------- custom ops
+@torch.library.custom_op("surgvid::evp_lfb_forward", mutates_args=())
+def evp_lfb_forward(x: torch.Tensor, seg: torch.Tensor, flow: Optional[torch.Tensor], handle: int, micro_batch: int) -> torch.Tensor:
+    """[B,3,H,W] frames + segmaps (+ [B,2,H,W] flow) -> [B, 2048] LFB features.
+    Replaces model_LFB.forward(inputs, segmaps, flow, return_features=True) (generate_evp_LFB.py:454)."""
+    owner = _HANDLES[handle]
+    return owner._native_forward(x, seg, flow, micro_batch)
+
+
+@evp_lfb_forward.register_fake
+def _(x, seg, flow, handle, micro_batch):
+    return x.new_empty((x.shape[0], _HANDLES[handle].embedding_dim), dtype=torch.float32)
+
+
+@torch.library.custom_op("surgvid::mstcn_forward", mutates_args=())
+def mstcn_forward(feats: torch.Tensor, offsets: torch.Tensor, handle: int) -> torch.Tensor:
+    """feats [T_total, f_dim] fp32 time-major, offsets int64 CPU [n_videos+1] -> logits [stages, out_features, T_total].
+    Replaces MultiStageModel_S.forward (mstcn.py:122-130; call site trans_SV_output.py:279)."""
+    owner = _HANDLES[handle]
+    return owner._native_forward(feats, offsets)
+
+
+@mstcn_forward.register_fake
+def _(feats, offsets, handle):
+    o = _HANDLES[handle]
+    return feats.new_empty((o.num_stages, o.num_classes, feats.shape[0]), dtype=torch.float32)
+
+
+def register_handle(owner) -> int:
+    hid = id(owner)
+    _HANDLES[hid] = owner
+    return hid
+
+
+def unregister_handle(hid: int):
+    _HANDLES.pop(hid, None)
+
+
+# ----------------------------------------------------------------------------------------------- single kernels
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
+              residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(a @ w.T + bias) (+ residual); a [M,K] bf16, w [N,K] bf16 (row strides may exceed K)."""
+    _require_cuda(a, w, bias, residual, out)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    assert out.stride(1) == 1 and out.dtype in (torch.bfloat16, torch.float32)
+    lib = _native.lib()
+    rc = lib.sv_op_gemm_bf16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, _ptr(bias), act, _ptr(residual),
+                             0 if residual is None else residual.stride(0), _ptr(out), out.stride(0), int(out.dtype == torch.float32),
+                             _stream_ptr(a.device))
+    _native.check(rc, "sv_op_gemm_bf16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_f32=False, want_bf16=True):
+    _require_cuda(x, gamma, beta)
+    rows, C = x.shape
+    of = torch.empty_like(x) if want_f32 else None
+    ob = torch.empty((rows, C), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    rc = _native.lib().sv_op_layernorm(_ptr(x), _ptr(gamma), _ptr(beta), eps, rows, C, _ptr(of), _ptr(ob), _stream_ptr(x.device))
+    _native.check(rc, "sv_op_layernorm")
+    return of, ob
+
+
+def im2col(src: torch.Tensor, k: int, stride: int, pad: int, ldo: Optional[int] = None) -> torch.Tensor:
+    """src: [B,Cin,H,W] fp32 (NCHW) or [B,H,W,Cin] bf16 (NHWC) -> [B*Ho*Wo, ldo] bf16, k index (kh,kw,cin)."""
+    _require_cuda(src)
+    if src.dtype == torch.float32:
+        B, Cin, H, W = src.shape
+    else:
+        B, H, W, Cin = src.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    K = k * k * Cin
+    ldo = ldo or (K + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, ldo), dtype=torch.bfloat16, device=src.device)
+    nchw, nhwc = (src, None) if src.dtype == torch.float32 else (None, src)
+    rc = _native.lib().sv_op_im2col(_ptr(nchw), _ptr(nhwc), B, Cin, H, W, k, stride, pad, _ptr(out), ldo, _stream_ptr(src.device))
+    _native.check(rc, "sv_op_im2col")
+    return out
+
+
+def dwconv3x3_gelu(x: torch.Tensor, w9c: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x [B,H,W,C] bf16 NHWC, w9c [9,C] fp32, bias [C] fp32 -> GELU(dwconv3x3(x)+bias) bf16."""
+    _require_cuda(x, w9c, bias)
+    B, H, W, C = x.shape
+    out = torch.empty_like(x)
+    rc = _native.lib().sv_op_dwconv3x3_gelu(_ptr(x), _ptr(w9c), _ptr(bias), B, H, W, C, _ptr(out), _stream_ptr(x.device))
+    _native.check(rc, "sv_op_dwconv3x3_gelu")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, hd: int, scale: float) -> torch.Tensor:
+    """q [B*Nq, >=heads*hd] bf16, k/v [B*Nkv, ...] bf16 (row-strided views allowed) -> o [B*Nq, heads*hd] bf16."""
+    _require_cuda(q, k, v)
+    Nq, Nkv = q.shape[0] // B, k.shape[0] // B
+    o = torch.empty((q.shape[0], heads * hd), dtype=torch.bfloat16, device=q.device)
+    rc = _native.lib().sv_op_attention(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _ptr(o), o.stride(0), B, heads, Nq, Nkv,
+                                       hd, scale, _stream_ptr(q.device))
+    _native.check(rc, "sv_op_attention")
+    return o
+
+
+def gauss5x5(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    rc = _native.lib().sv_op_gauss5x5(_ptr(x), _ptr(out), B * C, H, W, _stream_ptr(x.device))
+    _native.check(rc, "sv_op_gauss5x5")
+    return out
+
+
+def bilinear_tokens(x: torch.Tensor, Ho: int, Wo: int) -> torch.Tensor:
+    _require_cuda(x)
+    B, H, W, C = x.shape
+    out = torch.empty((B, Ho, Wo, C), dtype=torch.bfloat16, device=x.device)
+    rc = _native.lib().sv_op_bilinear_tokens(_ptr(x), B, H, W, C, Ho, Wo, _ptr(out), C, _stream_ptr(x.device))
+    _native.check(rc, "sv_op_bilinear_tokens")
+    return out
+
+
+def token_mean(x: torch.Tensor, tokens: int) -> torch.Tensor:
+    _require_cuda(x)
+    rows, C = x.shape
+    B = rows // tokens
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    rc = _native.lib().sv_op_token_mean(_ptr(x), B, tokens, C, _ptr(out), _stream_ptr(x.device))
+    _native.check(rc, "sv_op_token_mean")
+    return out
