@@ -126,6 +126,12 @@ struct sv_evp {
   std::map<long long, std::unique_ptr<sv::Plan>> plans;
   sv::Plan* last_plan = nullptr;
   int64_t launches = 0;
+  // optional per-kernel-class timing (CUDA events around every launch; bench.py's roofline pass)
+  bool profile = false;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_gemm_flops = 0.0;
+  std::vector<cudaEvent_t> prof_events;
 };
 
 namespace sv {
@@ -611,8 +617,18 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
 }
 
 int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const float* flow, float* out, cudaStream_t st) {
+  const bool prof = h->profile;
+  if (prof) {
+    while (h->prof_events.size() < 2 * p.ops.size()) {
+      cudaEvent_t e;
+      SV_CUDA_OK(cudaEventCreate(&e));
+      h->prof_events.push_back(e);
+    }
+  }
+  size_t op_idx = 0;
   for (const Op& op : p.ops) {
     int rc = SV_OK;
+    if (prof) SV_CUDA_OK(cudaEventRecord(h->prof_events[2 * op_idx], st));
     switch (op.kind) {
       case OP_GEMM: rc = gemm_launch(op.gemm, st); break;
       case OP_LN:
@@ -642,7 +658,19 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
       case OP_MEAN: rc = launch_token_mean(static_cast<const float*>(op.src), op.i[0], op.i[1], op.i[2], out, st); break;
     }
     if (rc != SV_OK) return rc;
+    if (prof) SV_CUDA_OK(cudaEventRecord(h->prof_events[2 * op_idx + 1], st));
+    ++op_idx;
     ++h->launches;
+  }
+  if (prof) {
+    SV_CUDA_OK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+      float ms = 0.f;
+      SV_CUDA_OK(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
+      h->prof_ms[p.ops[i].kind] += ms;
+      h->prof_n[p.ops[i].kind] += 1;
+    }
+    h->prof_gemm_flops += p.gemm_flops;
   }
   return SV_OK;
 }
@@ -798,5 +826,22 @@ int sv_evp_read_tap(sv_evp_handle* h, const char* name, float* dst, int64_t max_
 }
 
 int64_t sv_evp_last_launch_count(const sv_evp_handle* h) { return h ? h->launches : 0; }
+
+int sv_evp_set_profile(sv_evp_handle* h, int32_t enable) {
+  using namespace sv;
+  SV_CHECK(h, "null handle");
+  h->profile = enable != 0;
+  for (int i = 0; i < 8; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+  h->prof_gemm_flops = 0.0;
+  return SV_OK;
+}
+
+int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops) {
+  using namespace sv;
+  SV_CHECK(h && ms_by_kind && launches_by_kind && gemm_flops, "null argument");
+  for (int i = 0; i < 8; ++i) { ms_by_kind[i] = h->prof_ms[i]; launches_by_kind[i] = h->prof_n[i]; }
+  *gemm_flops = h->prof_gemm_flops;
+  return SV_OK;
+}
 
 }  // extern "C"

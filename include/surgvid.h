@@ -95,6 +95,14 @@ int sv_evp_read_tap(sv_evp_handle* h, const char* name, float* dst, int64_t max_
 /* number of kernels the last sv_evp_forward call launched (for bench.py's gpu_launches) */
 int64_t sv_evp_last_launch_count(const sv_evp_handle* h);
 
+/* Per-kernel-class device timing for roofline reports: when enabled, every launch of sv_evp_forward is bracketed by
+ * CUDA events on `stream` and the forward synchronises at the end of each micro-batch (never enable in a timed run).
+ * Classes (index): 0 tcgen05 GEMM, 1 LayerNorm, 2 im2col, 3 DWConv+GELU, 4 attention, 5 Gaussian, 6 bilinear, 7 token mean.
+ * sv_evp_set_profile resets the accumulators; sv_evp_get_profile fills ms_by_kind[8], launches_by_kind[8] and the
+ * algorithmic GEMM FLOPs (2*M*N*K summed over the GEMM launches) since the last reset. */
+int sv_evp_set_profile(sv_evp_handle* h, int32_t enable);
+int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops);
+
 /* ------------------------------------------------------------------------------------------------
  * MS-TCN MultiStageModel_S
  * replaces: mstcn.MultiStageModel_S(stages, layers, f_maps, f_dim, out_features, causal_conv)
