@@ -392,7 +392,8 @@ struct Builder {
   void gemm(const bf16* A, int64_t lda, const Lin& l, int M, int act, const float* resid, int64_t ldr, void* out, int64_t ldc, int out_fp32) {
     if (dry() || status != SV_OK) return;
     GemmDesc d;
-    d.A = A; d.lda = lda; d.W = W(l); d.ldw = l.ldw; d.M = M; d.N = l.N; d.K = l.K; d.bias = Bf(l); d.act = act;
+    d.A = A; d.lda = lda; d.W = W(l); d.ldw = l.ldw; d.M = M; d.N = l.N; d.bias = Bf(l); d.act = act;
+    d.K = l.ldw;  // K padded to a multiple of 8; pad columns are zero in both the packed weight and the im2col buffer
     d.residual = resid; d.ldr = ldr; d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
     Op op;
     op.kind = OP_GEMM;
