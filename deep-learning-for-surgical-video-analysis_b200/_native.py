@@ -22,7 +22,7 @@ SV_OK = 0
 EXPORTED_SYMBOLS = [
     "sv_last_error", "sv_abi_version",
     "sv_evp_create", "sv_evp_destroy", "sv_evp_set_tensor", "sv_evp_pack_weights", "sv_evp_workspace_bytes",
-    "sv_evp_forward", "sv_evp_classify", "sv_evp_read_tap", "sv_evp_last_launch_count", "sv_evp_set_profile", "sv_evp_get_profile",
+    "sv_evp_forward", "sv_evp_classify", "sv_evp_read_tap", "sv_evp_last_launch_count", "sv_evp_set_profile", "sv_evp_get_profile", "sv_evp_dump_profile",
     "sv_mstcn_create", "sv_mstcn_destroy", "sv_mstcn_set_tensor", "sv_mstcn_pack_weights", "sv_mstcn_workspace_bytes",
     "sv_mstcn_forward", "sv_mstcn_last_launch_count",
     "sv_op_gemm_bf16", "sv_op_layernorm", "sv_op_im2col", "sv_op_dwconv3x3_gelu", "sv_op_attention", "sv_op_gauss5x5",
@@ -99,6 +99,7 @@ def _declare(lib):
     lib.sv_evp_last_launch_count.restype = c_int64
     lib.sv_evp_set_profile.argtypes = [c_void_p, c_int32]
     lib.sv_evp_get_profile.argtypes = [c_void_p, POINTER(ctypes.c_double), i64p, POINTER(ctypes.c_double)]
+    lib.sv_evp_dump_profile.argtypes = [c_void_p, c_char_p]
     lib.sv_mstcn_create.argtypes = [POINTER(MstcnCfg), POINTER(c_void_p)]
     lib.sv_mstcn_destroy.argtypes = [c_void_p]
     lib.sv_mstcn_set_tensor.argtypes = [c_void_p, c_char_p, c_void_p, i64p, c_int32]

@@ -105,10 +105,25 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict
 }
 
 // NCHW fp32 source (network inputs: Cin = 3 or 2): one thread gathers 8 consecutive k indices (kh,kw,c order).
+// The k -> (plane offset, kh, kw) decomposition is tabulated once per block in shared memory (no div/mod per element).
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ src, int B, int Cin, int H, int W, int k, int stride,
                                                               int pad, int Ho, int Wo, bf16* __restrict__ out, int64_t ldo) {
+  __shared__ int tab_off[256];
+  __shared__ int tab_hw[256];
   const int K = k * k * Cin;
-  const int kchunks = static_cast<int>(ldo >> 3);
+  const int kpad = static_cast<int>(ldo);
+  for (int kk = threadIdx.x; kk < kpad; kk += blockDim.x) {
+    if (kk < K) {
+      const int c = kk % Cin, kw = (kk / Cin) % k, kh = kk / (Cin * k);
+      tab_off[kk] = (c * H + kh) * W + kw;
+      tab_hw[kk] = (kh << 16) | kw;
+    } else {
+      tab_off[kk] = 0;
+      tab_hw[kk] = -1;
+    }
+  }
+  __syncthreads();
+  const int kchunks = kpad >> 3;
   const int64_t total = static_cast<int64_t>(B) * Ho * Wo * kchunks;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -117,18 +132,17 @@ __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __res
   const int ow = static_cast<int>(m % Wo);
   const int oh = static_cast<int>((m / Wo) % Ho);
   const int b = static_cast<int>(m / (static_cast<int64_t>(Wo) * Ho));
+  const int ih0 = oh * stride - pad, iw0 = ow * stride - pad;
+  const float* sb = src + static_cast<int64_t>(b) * Cin * H * W + static_cast<int64_t>(ih0) * W + iw0;
   float f[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int kk = kc * 8 + j;
+    const int hw = tab_hw[kk];
     float val = 0.f;
-    if (kk < K) {
-      const int c = kk % Cin;
-      const int kw = (kk / Cin) % k;
-      const int kh = kk / (Cin * k);
-      const int ih = oh * stride - pad + kh;
-      const int iw = ow * stride - pad + kw;
-      if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(src + ((static_cast<int64_t>(b) * Cin + c) * H + ih) * W + iw);
+    if (hw >= 0) {
+      const int ih = ih0 + (hw >> 16), iw = iw0 + (hw & 0xffff);
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) val = __ldg(sb + tab_off[kk]);
     }
     f[j] = val;
   }
@@ -141,84 +155,68 @@ __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------ DWConv3x3 + bias + GELU
-// NHWC bf16; one thread owns 8 channels of a vertical run of R output pixels and slides a 3x3 window down the
-// column, so each input row segment is loaded once per thread and the 72 weights stay in registers.
+// NHWC bf16.  Block = 8 adjacent pixel columns (threadIdx.y) x 32 lanes of 4 channels (128 channels, 256 B per pixel):
+// each thread owns 4 channels of a vertical run of kDwRun output pixels and slides a 3x3 window down its column, so an
+// input row segment is loaded once per thread, the 36 weights stay in registers, and neighbouring columns (same block)
+// share their loads through L1.  Loads run one row ahead of the arithmetic.
 constexpr int kDwRun = 7;
+constexpr int kDwCols = 8;
 
-__device__ __forceinline__ void dw_load_row(const bf16* __restrict__ base, int hh, int w, int H, int W, int C, uint4 (&row)[3]) {
+__device__ __forceinline__ void dw_load_row(const bf16* __restrict__ base, int hh, int w, int H, int W, int C, uint2 (&row)[3]) {
 #pragma unroll
   for (int dx = 0; dx < 3; ++dx) {
     const int ww = w + dx - 1;
     if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      row[dx] = __ldg(reinterpret_cast<const uint4*>(base + (static_cast<int64_t>(hh) * W + ww) * C));
+      row[dx] = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<int64_t>(hh) * W + ww) * C));
     else
-      row[dx] = make_uint4(0u, 0u, 0u, 0u);
+      row[dx] = make_uint2(0u, 0u);
   }
 }
 
-__device__ __forceinline__ void dw_fma8(float (&acc)[8], const uint4& x, const float (&w)[8]) {
-  const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y), c = unpack_bf16x2(x.z), d = unpack_bf16x2(x.w);
-  acc[0] = fmaf(a.x, w[0], acc[0]); acc[1] = fmaf(a.y, w[1], acc[1]);
-  acc[2] = fmaf(b.x, w[2], acc[2]); acc[3] = fmaf(b.y, w[3], acc[3]);
-  acc[4] = fmaf(c.x, w[4], acc[4]); acc[5] = fmaf(c.y, w[5], acc[5]);
-  acc[6] = fmaf(d.x, w[6], acc[6]); acc[7] = fmaf(d.y, w[7], acc[7]);
+__device__ __forceinline__ void dw_fma4(float (&acc)[4], const uint2& x, const float4& w) {
+  const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y);
+  acc[0] = fmaf(a.x, w.x, acc[0]); acc[1] = fmaf(a.y, w.y, acc[1]);
+  acc[2] = fmaf(b.x, w.z, acc[2]); acc[3] = fmaf(b.y, w.w, acc[3]);
 }
 
-__global__ void __launch_bounds__(256) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
-                                                             const float* __restrict__ bias, int B, int H, int W, int C,
-                                                             bf16* __restrict__ out) {
-  const int cv = C >> 3;
+__global__ void __launch_bounds__(256, 3) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
+                                                                const float* __restrict__ bias, int B, int H, int W, int C,
+                                                                bf16* __restrict__ out) {
   const int hsegs = (H + kDwRun - 1) / kDwRun;
-  const int64_t total = static_cast<int64_t>(B) * hsegs * W * cv;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % cv);
-  int64_t t = idx / cv;
-  const int w = static_cast<int>(t % W); t /= W;
-  const int hs = static_cast<int>(t % hsegs);
-  const int b = static_cast<int>(t / hsegs);
-  const int c0 = c8 * 8;
+  const int c0 = (blockIdx.z * 32 + threadIdx.x) * 4;
+  const int w = blockIdx.x * kDwCols + threadIdx.y;
+  const int hs = blockIdx.y % hsegs;
+  const int b = blockIdx.y / hsegs;
+  if (c0 >= C || w >= W) return;
 
-  float wt[9][8];
+  float4 wt[9];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0 + 4));
-    wt[tap][0] = a.x; wt[tap][1] = a.y; wt[tap][2] = a.z; wt[tap][3] = a.w;
-    wt[tap][4] = bq.x; wt[tap][5] = bq.y; wt[tap][6] = bq.z; wt[tap][7] = bq.w;
-  }
-  float bs[8];
-  {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w; bs[4] = bq.x; bs[5] = bq.y; bs[6] = bq.z; bs[7] = bq.w;
-  }
+  for (int tap = 0; tap < 9; ++tap) wt[tap] = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0));
+  const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c0));
   const bf16* base = x + static_cast<int64_t>(b) * H * W * C + c0;
   bf16* obase = out + static_cast<int64_t>(b) * H * W * C + c0;
   const int h0 = hs * kDwRun;
   const int h1 = min(h0 + kDwRun, H);
-  uint4 prev[3], cur[3], next[3];
+  uint2 prev[3], cur[3], next[3];
   dw_load_row(base, h0 - 1, w, H, W, C, prev);
   dw_load_row(base, h0, w, H, W, C, cur);
+  dw_load_row(base, h0 + 1, w, H, W, C, next);
   for (int h = h0; h < h1; ++h) {
-    dw_load_row(base, h + 1, w, H, W, C, next);
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+    uint2 ahead[3];
+    dw_load_row(base, h + 2, w, H, W, C, ahead);  // in flight while this row is computed
+    float acc[4] = {bs.x, bs.y, bs.z, bs.w};
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx) {
-      dw_fma8(acc, prev[dx], wt[0 * 3 + dx]);
-      dw_fma8(acc, cur[dx], wt[1 * 3 + dx]);
-      dw_fma8(acc, next[dx], wt[2 * 3 + dx]);
+      dw_fma4(acc, prev[dx], wt[0 * 3 + dx]);
+      dw_fma4(acc, cur[dx], wt[1 * 3 + dx]);
+      dw_fma4(acc, next[dx], wt[2 * 3 + dx]);
     }
-    uint4 o;
-    o.x = pack_bf16x2(gelu_erf(acc[0]), gelu_erf(acc[1]));
-    o.y = pack_bf16x2(gelu_erf(acc[2]), gelu_erf(acc[3]));
-    o.z = pack_bf16x2(gelu_erf(acc[4]), gelu_erf(acc[5]));
-    o.w = pack_bf16x2(gelu_erf(acc[6]), gelu_erf(acc[7]));
-    *reinterpret_cast<uint4*>(obase + (static_cast<int64_t>(h) * W + w) * C) = o;
+    uint2 o;
+    o.x = pack_bf16x2(gelu_erf_fast(acc[0]), gelu_erf_fast(acc[1]));
+    o.y = pack_bf16x2(gelu_erf_fast(acc[2]), gelu_erf_fast(acc[3]));
+    *reinterpret_cast<uint2*>(obase + (static_cast<int64_t>(h) * W + w) * C) = o;
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) { prev[dx] = cur[dx]; cur[dx] = next[dx]; }
+    for (int dx = 0; dx < 3; ++dx) { prev[dx] = cur[dx]; cur[dx] = next[dx]; next[dx] = ahead[dx]; }
   }
 }
 
@@ -340,6 +338,7 @@ int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, i
   const int K = k * k * Cin;
   SV_CHECK(ldo % 8 == 0 && ldo >= K, "im2col ldo must be a multiple of 8 and >= k*k*Cin");
   if (src_nchw_f32 != nullptr) {
+    SV_CHECK(ldo <= 256, "im2col NCHW path supports k*k*Cin <= 256");
     const int64_t total = static_cast<int64_t>(B) * Ho * Wo * (ldo / 8);
     im2col_nchw_f32_kernel<<<blocks_for(total), 256, 0, st>>>(src_nchw_f32, B, Cin, H, W, k, stride, pad, Ho, Wo, out, ldo);
     return launch_status("im2col_nchw_f32_kernel");
@@ -352,9 +351,12 @@ int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, i
 }
 
 int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st) {
-  SV_CHECK(C % 8 == 0, "dwconv needs C%8==0");
-  const int64_t total = static_cast<int64_t>(B) * ceil_div(H, kDwRun) * W * (C / 8);
-  dwconv3x3_gelu_kernel<<<blocks_for(total), 256, 0, st>>>(x, w9c, bias, B, H, W, C, out);
+  SV_CHECK(C % 4 == 0, "dwconv needs C%4==0");
+  const int hsegs = ceil_div(H, kDwRun);
+  SV_CHECK(static_cast<int64_t>(B) * hsegs <= 65535 && ceil_div(C, 128) <= 65535, "dwconv grid limits");
+  dim3 grid(ceil_div(W, kDwCols), B * hsegs, ceil_div(C, 128));
+  dim3 block(32, kDwCols);
+  dwconv3x3_gelu_kernel<<<grid, block, 0, st>>>(x, w9c, bias, B, H, W, C, out);
   return launch_status("dwconv3x3_gelu_kernel");
 }
 

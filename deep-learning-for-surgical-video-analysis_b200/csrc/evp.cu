@@ -10,6 +10,7 @@
 // per (micro-batch, H, W, workspace) and replayed; frames are processed in micro-batches so the working set stays
 // in the 126 MB L2.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <map>
@@ -72,6 +73,8 @@ struct Op {
   int i[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   float f0 = 0.f;
   int ext_src = EXT_NONE, ext_dst = EXT_NONE;
+  mutable double prof_ms = 0.0;   // filled only in profiling mode
+  mutable long long prof_n = 0;
 };
 
 struct Tap {
@@ -670,6 +673,8 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
       SV_CUDA_OK(cudaEventElapsedTime(&ms, h->prof_events[2 * i], h->prof_events[2 * i + 1]));
       h->prof_ms[p.ops[i].kind] += ms;
       h->prof_n[p.ops[i].kind] += 1;
+      p.ops[i].prof_ms += ms;
+      p.ops[i].prof_n += 1;
     }
     h->prof_gemm_flops += p.gemm_flops;
   }
@@ -834,6 +839,33 @@ int sv_evp_set_profile(sv_evp_handle* h, int32_t enable) {
   h->profile = enable != 0;
   for (int i = 0; i < 8; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
   h->prof_gemm_flops = 0.0;
+  for (auto& kv : h->plans)
+    for (const Op& op : kv.second->ops) { op.prof_ms = 0.0; op.prof_n = 0; }
+  return SV_OK;
+}
+
+int sv_evp_dump_profile(const sv_evp_handle* h, const char* path) {
+  using namespace sv;
+  SV_CHECK(h && path, "null argument");
+  FILE* f = fopen(path, "w");
+  if (!f) return fail(SV_ERR_INVALID, std::string("cannot open ") + path);
+  static const char* kinds[] = {"gemm", "layernorm", "im2col", "dwconv", "attention", "gauss", "bilinear", "mean"};
+  fprintf(f, "plan_n,op,kind,M,N,K,block_n,stages,grid,act,out_fp32,resid,i0,i1,i2,i3,i4,calls,ms_total\n");
+  for (const auto& kv : h->plans) {
+    const Plan& p = *kv.second;
+    for (size_t i = 0; i < p.ops.size(); ++i) {
+      const Op& op = p.ops[i];
+      if (op.prof_n == 0) continue;
+      const GemmParams& g = op.gemm.p;
+      if (op.kind == OP_GEMM)
+        fprintf(f, "%d,%zu,%s,%d,%d,%d,%d,%d,%d,%d,%d,%d,0,0,0,0,0,%lld,%.6f\n", p.n, i, kinds[op.kind], g.M, g.N, g.K, g.block_n, g.num_stages,
+                op.gemm.grid, g.act, g.out_fp32, g.residual != nullptr, op.prof_n, op.prof_ms);
+      else
+        fprintf(f, "%d,%zu,%s,%lld,0,0,0,0,0,0,0,0,%d,%d,%d,%d,%d,%lld,%.6f\n", p.n, i, kinds[op.kind], static_cast<long long>(op.l0), op.i[0], op.i[1],
+                op.i[2], op.i[3], op.i[4], op.prof_n, op.prof_ms);
+    }
+  }
+  fclose(f);
   return SV_OK;
 }
 

@@ -3,7 +3,9 @@
 //   * operands staged global -> shared by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into an mbarrier ring,
 //   * tcgen05.mma (cta_group::1, kind::f16, M=128, N=block_n) issued by ONE thread, fp32 accumulators in TMEM,
 //   * two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1,
-//   * epilogue warps read TMEM with tcgen05.ld and fuse bias / GELU(erf) / ReLU / fp32 residual add / bf16 cast.
+//   * epilogue warps read TMEM with tcgen05.ld (thread = accumulator row), transpose 32x32 fp32 blocks through a
+//     per-warp shared-memory staging tile so that bias / GELU(erf) / ReLU / fp32 residual add / bf16 cast and the
+//     global loads+stores run with 8 lanes on one 128-byte row segment (4 full lines per warp instruction instead of 32).
 //
 // Every nn.Linear, patchified nn.Conv2d and 1x1 conv of the LFB path goes through this kernel
 // (reference: mix_transformer_evp.py:81-84 q/kv/proj, :37-40 fc1/fc2, :188 patch-embed conv, :89 sr conv,
@@ -31,6 +33,8 @@ constexpr int kTmemCols = 512;                    // 2 accumulator buffers x 256
 constexpr int kAccStride = 256;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSmemBudget = 196608;               // operand ring budget (bytes), + 1 KB alignment slack
+constexpr int kStageLd = 36;                      // epilogue staging row stride (floats): 32 columns + 4 pad (conflict-free)
+constexpr int kStagingBytes = 4 * 32 * kStageLd * 4;  // 4 epilogue warps x 32 rows x 36 floats
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
@@ -48,6 +52,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int stage_bytes = kATileBytes + b_tile_bytes;
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* staging = reinterpret_cast<float*>(smem + S * stage_bytes);  // epilogue transpose tiles live behind the operand ring
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -137,56 +142,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int n0 = (tile % p.num_n_tiles) * p.block_n;
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        const int n = n0 + c0;
-        if (n >= p.N) break;  // warp-uniform
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_row + static_cast<uint32_t>(c0), r);
+      float* stg = staging + (warp - 2) * (32 * kStageLd);
+      const int sub_row = lane >> 3;        // 4 rows per warp instruction
+      const int c4 = (lane & 7) * 4;        // 8 lanes x 4 columns = one 32-column row segment
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(c0), r);
         ptx::tmem_ld_wait();
-        if (row_ok) {
+        // thread `lane` owns accumulator row `lane` of this warp's 32-row slab: park it in the staging tile
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            const int ng = n + g * 8;
-            if (ng < p.N) {
-              float v[8];
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int n = n0 + c0 + c4;
+        const bool col_ok = (c0 + c4 < p.block_n) && (n < p.N);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        const int row_base = m0 + quarter * 32 + sub_row;
+        float4 res[8];
+        if (p.residual != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + ng));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + ng + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.act != ACT_NONE) {
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row = row_base + ps * 4;
+            res[ps] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + n)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-              }
-              if (p.residual != nullptr) {
-                const float* rp = p.residual + static_cast<long long>(row) * p.ldr + ng;
-                const float4 r0 = *reinterpret_cast<const float4*>(rp);
-                const float4 r1 = *reinterpret_cast<const float4*>(rp + 4);
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-              }
-              if (p.out_fp32) {
-                float* op = reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldc + ng;
-                *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(op + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else {
-                bf16* op = reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldc + ng;
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]);
-                o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]);
-                o.w = pack_bf16x2(v[6], v[7]);
-                *reinterpret_cast<uint4*>(op) = o;
-              }
+        for (int ps = 0; ps < 8; ++ps) {
+          const int row = row_base + ps * 4;
+          float4 v = *reinterpret_cast<const float4*>(stg + (ps * 4 + sub_row) * kStageLd + c4);
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (p.act != ACT_NONE) {
+            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+          }
+          if (p.residual != nullptr) { v.x += res[ps].x; v.y += res[ps].y; v.z += res[ps].z; v.w += res[ps].w; }
+          if (col_ok && row < p.M) {
+            if (p.out_fp32) {
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldc + n) = v;
+            } else {
+              uint2 o;
+              o.x = pack_bf16x2(v.x, v.y);
+              o.y = pack_bf16x2(v.z, v.w);
+              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldc + n) = o;
             }
           }
         }
+        __syncwarp();  // staging tile is rewritten by the next chunk
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -248,6 +253,11 @@ int encode_operand_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t
 int gemm_pick_block_n(int M, int N, int K, int num_sms) {
   // Candidates are legal UMMA N for M=128 (multiples of 16, <= 256).  Model: time ~ waves * (per-tile cost),
   // per-tile cost ~ fixed epilogue/pipeline overhead + N_tile * (k-blocks + epilogue share).
+  // Per-tile cycle model (per SM): the slowest of
+  //   MMA issue        2*c cycles per 64-deep k-block (tcgen05 floor 128*c/256 per K=16 instruction),
+  //   operand staging  (128 + c) * 128 bytes per k-block over ~48 B/cycle/SM of L2->SM bandwidth (A is re-read once per n-tile),
+  //   epilogue         ~6 cycles per accumulator column for the warp's 32-row slab + fixed latency,
+  // times the number of waves of the persistent grid.
   const int n_pad = round_up(N, 16);
   const int m_tiles = ceil_div(M, kBlockM);
   const int kb = ceil_div(K, kBlockK);
@@ -258,7 +268,10 @@ int gemm_pick_block_n(int M, int N, int K, int num_sms) {
     const int n_tiles = ceil_div(N, c);
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
     const long long waves = (tiles + num_sms - 1) / num_sms;
-    const double per_tile = 48.0 + c * (0.5 * kb + 1.0);  // MMA ~ c/2 "units" per k-block, epilogue ~ c units
+    const double mma = 2.0 * c * kb;
+    const double load = (128.0 + c) * 128.0 * kb / 48.0;
+    const double epi = 6.0 * round_up(c, 32) + 400.0;
+    const double per_tile = std::max(mma, std::max(load, epi)) + 150.0;
     const double cost = waves * per_tile;
     if (cost < best_cost - 1e-9) { best_cost = cost; best = c; }
   }
@@ -285,7 +298,7 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.act = d.act; p.out_fp32 = d.out_fp32;
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.out = d.out; p.ldc = d.ldc;
   plan->grid = std::min(p.num_tiles, sms);
-  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes + 1024;
+  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes + kStagingBytes + 1024;
   plan->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K, d.lda, kBlockM));
   SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, p.block_n));
@@ -296,7 +309,7 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + 1024);
+    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kStagingBytes + 1024);
   });
   if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(attr_err));
   gemm_bf16_tcgen05_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_w, plan.p);

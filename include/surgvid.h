@@ -102,6 +102,8 @@ int64_t sv_evp_last_launch_count(const sv_evp_handle* h);
  * algorithmic GEMM FLOPs (2*M*N*K summed over the GEMM launches) since the last reset. */
 int sv_evp_set_profile(sv_evp_handle* h, int32_t enable);
 int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops);
+/* CSV with one line per launch of the schedule (shape, tile configuration, accumulated device ms) since the last reset. */
+int sv_evp_dump_profile(const sv_evp_handle* h, const char* path);
 
 /* ------------------------------------------------------------------------------------------------
  * MS-TCN MultiStageModel_S
