@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 #include "ptx.cuh"
@@ -35,7 +36,61 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSmemBudget = 196608;               // operand ring budget (bytes), + 1 KB alignment slack
 constexpr int kStageLd = 36;                      // epilogue staging row stride (floats): 32 columns + 4 pad (conflict-free)
 constexpr int kStagingBytes = 4 * 32 * kStageLd * 4;  // 4 epilogue warps x 32 rows x 36 floats
+constexpr int kBiasBytes = 4 * 256 * 4;           // per epilogue warp: this tile's 256 bias values
+constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
 
+// residual rows for one 32-column chunk: 8 passes x (4 rows x 8 lanes x float4)
+template <bool RESID>
+__device__ __forceinline__ void epi_load_residual(float4 (&res)[8], const GemmParams& p, int row_base, int n, bool col_ok) {
+  if constexpr (RESID) {
+#pragma unroll
+    for (int ps = 0; ps < 8; ++ps) {
+      const int row = row_base + ps * 4;
+      res[ps] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + n)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+// accumulator registers (thread = row) -> staging tile (transpose point)
+__device__ __forceinline__ void epi_park(float* stg, int lane, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
+        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+}
+
+// staging tile -> bias / activation / residual / cast -> global, 8 lanes per 128-byte row segment
+template <int ACT, bool OUT_F32, bool RESID>
+__device__ __forceinline__ void epi_store(const GemmParams& p, const float* stg, const float* bias_s, const float4 (&res)[8], int row_base,
+                                          int n, int c_local, bool col_ok, int sub_row, int c4) {
+  const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c_local);
+#pragma unroll
+  for (int ps = 0; ps < 8; ++ps) {
+    const int row = row_base + ps * 4;
+    float4 v = *reinterpret_cast<const float4*>(stg + (ps * 4 + sub_row) * kStageLd + c4);
+    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+    if constexpr (ACT == ACT_GELU) {
+      if constexpr (OUT_F32) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+      else { v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w); }
+    } else if constexpr (ACT == ACT_RELU) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    if constexpr (RESID) { v.x += res[ps].x; v.y += res[ps].y; v.z += res[ps].z; v.w += res[ps].w; }
+    if (col_ok && row < p.M) {
+      if constexpr (OUT_F32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldc + n) = v;
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldc + n) = o;
+      }
+    }
+  }
+}
+
+template <int ACT, bool OUT_F32, bool RESID>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -53,6 +108,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   // 128B swizzle needs 1024-byte aligned tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   float* staging = reinterpret_cast<float*>(smem + S * stage_bytes);  // epilogue transpose tiles live behind the operand ring
+  float* bias_smem = staging + 4 * 32 * kStageLd;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -135,67 +191,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    float* stg = staging + (warp - 2) * (32 * kStageLd);
+    float* bias_s = bias_smem + (warp - 2) * 256;
+    const int sub_row = lane >> 3;  // 4 rows per warp instruction
+    const int c4 = (lane & 7) * 4;  // 8 lanes x 4 columns = one 32-column row segment
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * kBlockM;
       const int n0 = (tile % p.num_n_tiles) * p.block_n;
+      const int n_valid = min(p.block_n, p.N - n0);
+      const int nchunks = (n_valid + 31) >> 5;
+      const int row_base = m0 + quarter * 32 + sub_row;
+      // while the MMAs of this tile are still running: bias slice -> smem, first residual rows -> registers
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = i * 128 + lane * 4;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && c < n_valid) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
+        *reinterpret_cast<float4*>(bias_s + c) = b;
+      }
+      float4 res_a[8], res_b[8];
+      epi_load_residual<RESID>(res_a, p, row_base, n0 + c4, c4 < n_valid);
+      __syncwarp();
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
-      float* stg = staging + (warp - 2) * (32 * kStageLd);
-      const int sub_row = lane >> 3;        // 4 rows per warp instruction
-      const int c4 = (lane & 7) * 4;        // 8 lanes x 4 columns = one 32-column row segment
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        if (n0 + c0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(c0), r);
+      uint32_t r_a[32], r_b[32];
+      ptx::tmem_ld_x32(t_row, r_a);
+      // two-deep software pipeline over 32-column chunks: TMEM load + residual load of chunk c+1 overlap the stores of chunk c
+      for (int c = 0; c < nchunks; c += 2) {
         ptx::tmem_ld_wait();
-        // thread `lane` owns accumulator row `lane` of this warp's 32-row slab: park it in the staging tile
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
-              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        epi_park(stg, lane, r_a);
+        if (c + 1 < nchunks) {
+          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 1) * 32), r_b);
+          epi_load_residual<RESID>(res_b, p, row_base, n0 + (c + 1) * 32 + c4, (c + 1) * 32 + c4 < n_valid);
+        } else {
+          ptx::tc_fence_before();  // the whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
         __syncwarp();
-        const int n = n0 + c0 + c4;
-        const bool col_ok = (c0 + c4 < p.block_n) && (n < p.N);
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok && p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        const int row_base = m0 + quarter * 32 + sub_row;
-        float4 res[8];
-        if (p.residual != nullptr) {
-#pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = row_base + ps * 4;
-            res[ps] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + n)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_a, row_base, n0 + c * 32 + c4, c * 32 + c4, c * 32 + c4 < n_valid, sub_row, c4);
+        __syncwarp();
+        if (c + 1 >= nchunks) break;
+        ptx::tmem_ld_wait();
+        epi_park(stg, lane, r_b);
+        if (c + 2 < nchunks) {
+          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 2) * 32), r_a);
+          epi_load_residual<RESID>(res_a, p, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid);
+        } else {
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-#pragma unroll
-        for (int ps = 0; ps < 8; ++ps) {
-          const int row = row_base + ps * 4;
-          float4 v = *reinterpret_cast<const float4*>(stg + (ps * 4 + sub_row) * kStageLd + c4);
-          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-          if (p.act != ACT_NONE) {
-            v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act); v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-          }
-          if (p.residual != nullptr) { v.x += res[ps].x; v.y += res[ps].y; v.z += res[ps].z; v.w += res[ps].w; }
-          if (col_ok && row < p.M) {
-            if (p.out_fp32) {
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldc + n) = v;
-            } else {
-              uint2 o;
-              o.x = pack_bf16x2(v.x, v.y);
-              o.y = pack_bf16x2(v.z, v.w);
-              *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldc + n) = o;
-            }
-          }
-        }
-        __syncwarp();  // staging tile is rewritten by the next chunk
+        __syncwarp();
+        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_b, row_base, n0 + (c + 1) * 32 + c4, (c + 1) * 32 + c4, (c + 1) * 32 + c4 < n_valid,
+                                       sub_row, c4);
+        __syncwarp();
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -298,21 +350,47 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.act = d.act; p.out_fp32 = d.out_fp32;
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.out = d.out; p.ldc = d.ldc;
   plan->grid = std::min(p.num_tiles, sms);
-  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes + kStagingBytes + 1024;
+  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes + kEpiSmemBytes + 1024;
   plan->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K, d.lda, kBlockM));
   SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, p.block_n));
   return SV_OK;
 }
 
+namespace {
+
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+
+template <int ACT>
+GemmKernelFn pick_kernel(int out_fp32, bool resid) {
+  if (out_fp32) return resid ? gemm_bf16_tcgen05_kernel<ACT, true, true> : gemm_bf16_tcgen05_kernel<ACT, true, false>;
+  return resid ? gemm_bf16_tcgen05_kernel<ACT, false, true> : gemm_bf16_tcgen05_kernel<ACT, false, false>;
+}
+
+GemmKernelFn kernel_for(const GemmParams& p) {
+  const bool resid = p.residual != nullptr;
+  switch (p.act) {
+    case ACT_GELU: return pick_kernel<ACT_GELU>(p.out_fp32, resid);
+    case ACT_RELU: return pick_kernel<ACT_RELU>(p.out_fp32, resid);
+    default: return pick_kernel<ACT_NONE>(p.out_fp32, resid);
+  }
+}
+
+}  // namespace
+
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kStagingBytes + 1024);
-  });
-  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(attr_err));
-  gemm_bf16_tcgen05_kernel<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_w, plan.p);
+  static std::mutex mu;
+  static std::vector<const void*> configured;
+  GemmKernelFn fn = kernel_for(plan.p);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (std::find(configured.begin(), configured.end(), reinterpret_cast<const void*>(fn)) == configured.end()) {
+      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kEpiSmemBytes + 1024);
+      if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
+      configured.push_back(reinterpret_cast<const void*>(fn));
+    }
+  }
+  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_w, plan.p);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
