@@ -11,8 +11,9 @@
 // (reference: mix_transformer_evp.py:81-84 q/kv/proj, :37-40 fc1/fc2, :188 patch-embed conv, :89 sr conv,
 // :599-642 adapter linears, :823-835 flow convs, :868 MHA projections; segformer_head.py:39,74 head).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (a warp may only touch TMEM lanes 32*(warp%4) .. +31, so 4 consecutive warps cover the 128 accumulator rows).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
+// (a warp may only touch TMEM lanes 32*(warp%4) .. +31; two warps share each lane quarter and split the 32-column chunks,
+// so every SM sub-partition has two epilogue warps to hide each other's latencies).
 #include <stdio.h>
 
 #include <algorithm>
@@ -29,14 +30,15 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 bf16 = 128 B = one swizzle row
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quarter, interleaved over 32-column chunks
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;                    // 2 accumulator buffers x 256 columns
 constexpr int kAccStride = 256;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kSmemBudget = 196608;               // operand ring budget (bytes), + 1 KB alignment slack
+constexpr int kSmemBudget = 184320;               // operand ring budget (bytes), + 1 KB alignment slack
 constexpr int kStageLd = 36;                      // epilogue staging row stride (floats): 32 columns + 4 pad (conflict-free)
-constexpr int kStagingBytes = 4 * 32 * kStageLd * 4;  // 4 epilogue warps x 32 rows x 36 floats
-constexpr int kBiasBytes = 4 * 256 * 4;           // per epilogue warp: this tile's 256 bias values
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageLd * 4;  // per epilogue warp: 32 rows x 36 floats
+constexpr int kBiasBytes = kEpiWarps * 256 * 4;   // per epilogue warp: this tile's 256 bias values
 constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
 
 // residual rows for one 32-column chunk: 8 passes x (4 rows x 8 lanes x float4)
@@ -65,6 +67,8 @@ template <int ACT, bool OUT_F32, bool RESID>
 __device__ __forceinline__ void epi_store(const GemmParams& p, const float* stg, const float* bias_s, const float4 (&res)[8], int row_base,
                                           int n, int c_local, bool col_ok, int sub_row, int c4) {
   const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c_local);
+  const long long out_off = static_cast<long long>(row_base) * p.ldc + n;
+  const long long row_step = 4 * p.ldc;
 #pragma unroll
   for (int ps = 0; ps < 8; ++ps) {
     const int row = row_base + ps * 4;
@@ -79,12 +83,12 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, const float* stg,
     if constexpr (RESID) { v.x += res[ps].x; v.y += res[ps].y; v.z += res[ps].z; v.w += res[ps].w; }
     if (col_ok && row < p.M) {
       if constexpr (OUT_F32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(row) * p.ldc + n) = v;
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + ps * row_step) = v;
       } else {
         uint2 o;
         o.x = pack_bf16x2(v.x, v.y);
         o.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + static_cast<long long>(row) * p.ldc + n) = o;
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + out_off + ps * row_step) = o;
       }
     }
   }
@@ -106,9 +110,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int b_tile_bytes = p.block_n * kBlockK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;
   // 128B swizzle needs 1024-byte aligned tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // (offset arithmetic on the __shared__ array keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + S * stage_bytes);  // epilogue transpose tiles live behind the operand ring
-  float* bias_smem = staging + 4 * 32 * kStageLd;
+  float* bias_smem = staging + kEpiWarps * 32 * kStageLd;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -122,7 +127,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full_bar[a], 1);
-        ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrive per epilogue warp
+        ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
       }
       ptx::fence_barrier_init();
     }
@@ -190,7 +195,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // 0: even 32-column chunks, 1: odd chunks
     float* stg = staging + (warp - 2) * (32 * kStageLd);
     float* bias_s = bias_smem + (warp - 2) * 256;
     const int sub_row = lane >> 3;  // 4 rows per warp instruction
@@ -212,42 +218,41 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         *reinterpret_cast<float4*>(bias_s + c) = b;
       }
       float4 res_a[8], res_b[8];
-      epi_load_residual<RESID>(res_a, p, row_base, n0 + c4, c4 < n_valid);
+      epi_load_residual<RESID>(res_a, p, row_base, n0 + half * 32 + c4, half * 32 + c4 < n_valid);
       __syncwarp();
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
       uint32_t r_a[32], r_b[32];
-      ptx::tmem_ld_x32(t_row, r_a);
-      // two-deep software pipeline over 32-column chunks: TMEM load + residual load of chunk c+1 overlap the stores of chunk c
-      for (int c = 0; c < nchunks; c += 2) {
+      if (half < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(half * 32), r_a);
+      // two-deep software pipeline over this warp's chunks (c, c+2, ...): the TMEM load and residual load of the next chunk
+      // overlap the stores of the current one
+      for (int c = half; c < nchunks; c += 4) {
         ptx::tmem_ld_wait();
         epi_park(stg, lane, r_a);
-        if (c + 1 < nchunks) {
-          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 1) * 32), r_b);
-          epi_load_residual<RESID>(res_b, p, row_base, n0 + (c + 1) * 32 + c4, (c + 1) * 32 + c4 < n_valid);
-        } else {
-          ptx::tc_fence_before();  // the whole accumulator is in registers: hand the TMEM buffer back to the MMA warp
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        if (c + 2 < nchunks) {
+          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 2) * 32), r_b);
+          epi_load_residual<RESID>(res_b, p, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid);
         }
         __syncwarp();
         epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_a, row_base, n0 + c * 32 + c4, c * 32 + c4, c * 32 + c4 < n_valid, sub_row, c4);
         __syncwarp();
-        if (c + 1 >= nchunks) break;
+        if (c + 2 >= nchunks) break;
         ptx::tmem_ld_wait();
         epi_park(stg, lane, r_b);
-        if (c + 2 < nchunks) {
-          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 2) * 32), r_a);
-          epi_load_residual<RESID>(res_a, p, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid);
-        } else {
-          ptx::tc_fence_before();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        if (c + 4 < nchunks) {
+          ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 4) * 32), r_a);
+          epi_load_residual<RESID>(res_a, p, row_base, n0 + (c + 4) * 32 + c4, (c + 4) * 32 + c4 < n_valid);
         }
         __syncwarp();
-        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_b, row_base, n0 + (c + 1) * 32 + c4, (c + 1) * 32 + c4, (c + 1) * 32 + c4 < n_valid,
+        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_b, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid,
                                        sub_row, c4);
         __syncwarp();
       }
+      // every TMEM read of this warp has completed (the last tcgen05.wait::ld is behind us): release the accumulator
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
