@@ -155,31 +155,29 @@ __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------------ DWConv3x3 + bias + GELU
-// NHWC bf16.  Block = 8 adjacent pixel columns (threadIdx.y) x 32 lanes of 4 channels (128 channels, 256 B per pixel):
-// each thread owns 4 channels of a vertical run of kDwRun output pixels and slides a 3x3 window down its column, so an
-// input row segment is loaded once per thread, the 36 weights stay in registers, and neighbouring columns (same block)
-// share their loads through L1.  Loads run one row ahead of the arithmetic.
+// NHWC bf16.  Block = 8 adjacent pixel columns (threadIdx.y) x 32 lanes of 4 channels (128 channels, 256 B per pixel).
+// A thread owns 4 channels (two packed fp32x2 lanes) of a vertical run of kDwRun output pixels and slides a 3x3 window
+// down its column: each input row segment is loaded and unpacked to fp32 ONCE, the 36 weights stay in registers, the
+// arithmetic is FFMA2 (two fp32 lanes per instruction) and the GELU is MUFU-free, so the kernel stays close to its HBM
+// bound instead of the issue bound.  Row loop fully unrolled over a 4-slot register ring (loads run one row ahead).
 constexpr int kDwRun = 7;
 constexpr int kDwCols = 8;
 
-__device__ __forceinline__ void dw_load_row(const bf16* __restrict__ base, int hh, int w, int H, int W, int C, uint2 (&row)[3]) {
-#pragma unroll
-  for (int dx = 0; dx < 3; ++dx) {
-    const int ww = w + dx - 1;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      row[dx] = __ldg(reinterpret_cast<const uint2*>(base + (static_cast<int64_t>(hh) * W + ww) * C));
-    else
-      row[dx] = make_uint2(0u, 0u);
-  }
+struct DwRow { f32x2 v[3][2]; };  // 3 columns (w-1, w, w+1) x 2 channel pairs
+
+__device__ __forceinline__ void dw_load_row(DwRow& r, const bf16* __restrict__ base, int hh, int H, int W, int C, int w, bool lok, bool rok) {
+  const bool hok = hh >= 0 && hh < H;
+  const bf16* p = base + (static_cast<int64_t>(hh) * W + w) * C;
+  uint2 a = make_uint2(0u, 0u), b = make_uint2(0u, 0u), c = make_uint2(0u, 0u);
+  if (hok && lok) a = __ldg(reinterpret_cast<const uint2*>(p - C));
+  if (hok) b = __ldg(reinterpret_cast<const uint2*>(p));
+  if (hok && rok) c = __ldg(reinterpret_cast<const uint2*>(p + C));
+  r.v[0][0] = f2_from_bf16x2(a.x); r.v[0][1] = f2_from_bf16x2(a.y);
+  r.v[1][0] = f2_from_bf16x2(b.x); r.v[1][1] = f2_from_bf16x2(b.y);
+  r.v[2][0] = f2_from_bf16x2(c.x); r.v[2][1] = f2_from_bf16x2(c.y);
 }
 
-__device__ __forceinline__ void dw_fma4(float (&acc)[4], const uint2& x, const float4& w) {
-  const float2 a = unpack_bf16x2(x.x), b = unpack_bf16x2(x.y);
-  acc[0] = fmaf(a.x, w.x, acc[0]); acc[1] = fmaf(a.y, w.y, acc[1]);
-  acc[2] = fmaf(b.x, w.z, acc[2]); acc[3] = fmaf(b.y, w.w, acc[3]);
-}
-
-__global__ void __launch_bounds__(256, 3) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
+__global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
                                                                 const float* __restrict__ bias, int B, int H, int W, int C,
                                                                 bf16* __restrict__ out) {
   const int hsegs = (H + kDwRun - 1) / kDwRun;
@@ -189,34 +187,48 @@ __global__ void __launch_bounds__(256, 3) dwconv3x3_gelu_kernel(const bf16* __re
   const int b = blockIdx.y / hsegs;
   if (c0 >= C || w >= W) return;
 
-  float4 wt[9];
+  f32x2 wt[9][2];
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) wt[tap] = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0));
+  for (int tap = 0; tap < 9; ++tap) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w9c + tap * C + c0));
+    wt[tap][0] = f2_pack(t.x, t.y);
+    wt[tap][1] = f2_pack(t.z, t.w);
+  }
   const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c0));
+  const f32x2 bias0 = f2_pack(bs.x, bs.y), bias1 = f2_pack(bs.z, bs.w);
   const bf16* base = x + static_cast<int64_t>(b) * H * W * C + c0;
-  bf16* obase = out + static_cast<int64_t>(b) * H * W * C + c0;
+  bf16* obase = out + (static_cast<int64_t>(b) * H * W + w) * C + c0;
   const int h0 = hs * kDwRun;
-  const int h1 = min(h0 + kDwRun, H);
-  uint2 prev[3], cur[3], next[3];
-  dw_load_row(base, h0 - 1, w, H, W, C, prev);
-  dw_load_row(base, h0, w, H, W, C, cur);
-  dw_load_row(base, h0 + 1, w, H, W, C, next);
-  for (int h = h0; h < h1; ++h) {
-    uint2 ahead[3];
-    dw_load_row(base, h + 2, w, H, W, C, ahead);  // in flight while this row is computed
-    float acc[4] = {bs.x, bs.y, bs.z, bs.w};
+  const bool lok = w > 0, rok = w + 1 < W;
+  DwRow ring[4];
+  dw_load_row(ring[0], base, h0 - 1, H, W, C, w, lok, rok);
+  dw_load_row(ring[1], base, h0, H, W, C, w, lok, rok);
+  dw_load_row(ring[2], base, h0 + 1, H, W, C, w, lok, rok);
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      dw_fma4(acc, prev[dx], wt[0 * 3 + dx]);
-      dw_fma4(acc, cur[dx], wt[1 * 3 + dx]);
-      dw_fma4(acc, next[dx], wt[2 * 3 + dx]);
+  for (int i = 0; i < kDwRun; ++i) {
+    const int h = h0 + i;
+    if (h < H) {  // uniform per thread; rows beyond the image are never stored
+      if (i + 1 < kDwRun) dw_load_row(ring[(i + 3) & 3], base, h + 2, H, W, C, w, lok, rok);  // in flight during this row
+      const DwRow& r0 = ring[i & 3];
+      const DwRow& r1 = ring[(i + 1) & 3];
+      const DwRow& r2 = ring[(i + 2) & 3];
+      f32x2 a0 = bias0, a1 = bias1;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        a0 = f2_fma(r0.v[dx][0], wt[dx][0], a0);     a1 = f2_fma(r0.v[dx][1], wt[dx][1], a1);
+        a0 = f2_fma(r1.v[dx][0], wt[3 + dx][0], a0); a1 = f2_fma(r1.v[dx][1], wt[3 + dx][1], a1);
+        a0 = f2_fma(r2.v[dx][0], wt[6 + dx][0], a0); a1 = f2_fma(r2.v[dx][1], wt[6 + dx][1], a1);
+      }
+      a0 = f2_gelu_erf_poly(a0);
+      a1 = f2_gelu_erf_poly(a1);
+      float y0, y1, y2, y3;
+      f2_unpack(a0, y0, y1);
+      f2_unpack(a1, y2, y3);
+      uint2 o;
+      o.x = pack_bf16x2(y0, y1);
+      o.y = pack_bf16x2(y2, y3);
+      *reinterpret_cast<uint2*>(obase + static_cast<int64_t>(h) * W * C) = o;
     }
-    uint2 o;
-    o.x = pack_bf16x2(gelu_erf_fast(acc[0]), gelu_erf_fast(acc[1]));
-    o.y = pack_bf16x2(gelu_erf_fast(acc[2]), gelu_erf_fast(acc[3]));
-    *reinterpret_cast<uint2*>(obase + (static_cast<int64_t>(h) * W + w) * C) = o;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) { prev[dx] = cur[dx]; cur[dx] = next[dx]; next[dx] = ahead[dx]; }
   }
 }
 
