@@ -1,0 +1,200 @@
+// Depthwise 3x3 (zero pad 1) + bias + GELU(erf) on NHWC bf16 — the middle of MixFFN (mix_transformer_evp.py:22-30, 63).
+//
+// HBM-bound op (read + write the 4C-wide hidden once).  Persistent, warp-specialised kernel:
+//   * one producer warp streams (TH+2) x (TW+2) x 128-channel input tiles (halo included) into a shared-memory ring with
+//     4-D TMA loads; TMA zero-fills coordinates outside the image, which IS the conv's zero padding and also keeps the
+//     frames of a batch from bleeding into each other (the frame index is its own tensor dimension);
+//   * eight consumer warps (warp = output column, lane = 4 channels) slide a 3x3 register window down their column,
+//     FFMA2 arithmetic, MUFU-free GELU, 256-byte coalesced stores.
+// Many tiles are in flight per SM regardless of register pressure, which the register-only version could not do.
+#include <mutex>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace sv {
+namespace {
+
+constexpr int kTW = 8;          // output columns per tile (= consumer warps)
+constexpr int kTH = 7;          // output rows per tile
+constexpr int kCB = 128;        // channels per tile (32 lanes x 4)
+constexpr int kStages = 3;
+constexpr int kBoxW = kTW + 2, kBoxH = kTH + 2;
+constexpr int kTileBytes = kBoxH * kBoxW * kCB * 2;  // 23 040
+constexpr int kThreads = 32 * (1 + kTW);
+
+struct DwParams {
+  const float* w9c;
+  const float* bias;
+  bf16* out;
+  int B, H, W, C;
+  int tiles_x, tiles_y, cblks;
+  long long num_tiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tmap_x);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], kTW);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  const long long tiles_per_cblk = static_cast<long long>(p.B) * p.tiles_y * p.tiles_x;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int cblk = static_cast<int>(t / tiles_per_cblk);
+        long long r = t % tiles_per_cblk;
+        const int tx = static_cast<int>(r % p.tiles_x); r /= p.tiles_x;
+        const int ty = static_cast<int>(r % p.tiles_y);
+        const int b = static_cast<int>(r / p.tiles_y);
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], kTileBytes);
+        ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * kTW - 1, ty * kTH - 1, b);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ consumers: warp -> column, lane -> 4 channels
+    const int col = warp - 1;
+    int stage = 0;
+    uint32_t phase = 0;
+    int cur_cblk = -1;
+    f32x2 wt[9][2];
+    f32x2 bias0 = 0, bias1 = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int cblk = static_cast<int>(t / tiles_per_cblk);
+      long long r = t % tiles_per_cblk;
+      const int tx = static_cast<int>(r % p.tiles_x); r /= p.tiles_x;
+      const int ty = static_cast<int>(r % p.tiles_y);
+      const int b = static_cast<int>(r / p.tiles_y);
+      const int c0 = cblk * kCB + lane * 4;
+      if (cblk != cur_cblk) {  // weights of this 128-channel block stay in registers across tiles
+        cur_cblk = cblk;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w9c + tap * p.C + c0));
+          wt[tap][0] = f2_pack(w4.x, w4.y);
+          wt[tap][1] = f2_pack(w4.z, w4.w);
+        }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+        bias0 = f2_pack(b4.x, b4.y);
+        bias1 = f2_pack(b4.z, b4.w);
+      }
+      const int w = tx * kTW + col;
+      const int h0 = ty * kTH;
+      ptx::mbar_wait(&full_bar[stage], phase);
+      // smem tile: [kBoxH][kBoxW][128 ch] bf16; this thread reads box columns col, col+1, col+2
+      const uint2* tile = reinterpret_cast<const uint2*>(smem + stage * kTileBytes) + col * (kCB / 4) + lane;
+      auto load_row = [&](int br, f32x2 (&dst)[3][2]) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint2 v = tile[(br * kBoxW + dx) * (kCB / 4)];
+          dst[dx][0] = f2_from_bf16x2(v.x);
+          dst[dx][1] = f2_from_bf16x2(v.y);
+        }
+      };
+      f32x2 ring[3][3][2];
+      load_row(0, ring[0]);
+      load_row(1, ring[1]);
+      bf16* obase = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.C + c0;
+      const bool col_ok = w < p.W;
+#pragma unroll
+      for (int i = 0; i < kTH; ++i) {
+        load_row(i + 2, ring[(i + 2) % 3]);
+        f32x2 a0 = bias0, a1 = bias1;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            a0 = f2_fma(ring[(i + dy) % 3][dx][0], wt[dy * 3 + dx][0], a0);
+            a1 = f2_fma(ring[(i + dy) % 3][dx][1], wt[dy * 3 + dx][1], a1);
+          }
+        }
+        a0 = f2_gelu_erf_poly(a0);
+        a1 = f2_gelu_erf_poly(a1);
+        float y0, y1, y2, y3;
+        f2_unpack(a0, y0, y1);
+        f2_unpack(a1, y2, y3);
+        if (col_ok && h0 + i < p.H) {
+          uint2 o;
+          o.x = pack_bf16x2(y0, y1);
+          o.y = pack_bf16x2(y2, y3);
+          *reinterpret_cast<uint2*>(obase + static_cast<long long>(i) * p.W * p.C) = o;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);  // this warp is done reading the stage
+      if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+}  // namespace
+
+bool dwconv_tma_supported(int C) { return C % kCB == 0; }
+
+int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, DwconvPlan* plan) {
+  SV_CHECK(dwconv_tma_supported(C), "dwconv TMA path needs C % 128 == 0");
+  SV_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "dwconv alignment");
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point unavailable");
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {kCB, kBoxW, kBoxH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(dwconv) failed, CUresult " + std::to_string(static_cast<int>(r)));
+  plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C;
+  return SV_OK;
+}
+
+int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  constexpr int smem_bytes = kStages * kTileBytes + 128;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dwconv3x3_gelu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); });
+  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(attr_err));
+  DwParams p;
+  p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C;
+  p.tiles_x = ceil_div(plan.W, kTW); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
+  p.num_tiles = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
+  const int sms = device_sm_count();
+  const int grid = static_cast<int>(std::min<long long>(p.num_tiles, 2LL * sms));
+  dwconv3x3_gelu_tma_kernel<<<grid, kThreads, smem_bytes, st>>>(plan.tmap, p);
+  return launch_status("dwconv3x3_gelu_tma_kernel");
+}
+
+}  // namespace sv

@@ -363,6 +363,11 @@ int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, i
 }
 
 int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st) {
+  if (dwconv_tma_supported(C)) {  // main path: TMA halo staging (dwconv_tma.cu); the register-window kernel below covers C % 128 != 0
+    DwconvPlan plan;
+    SV_TRY(dwconv_tma_plan(x, w9c, bias, B, H, W, C, out, &plan));
+    return dwconv_tma_launch(plan, st);
+  }
   SV_CHECK(C % 4 == 0, "dwconv needs C%4==0");
   const int hsegs = ceil_div(H, kDwRun);
   SV_CHECK(static_cast<int64_t>(B) * hsegs <= 65535 && ceil_div(C, 128) <= 65535, "dwconv grid limits");

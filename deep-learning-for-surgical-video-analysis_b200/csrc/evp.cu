@@ -61,6 +61,8 @@ enum Ext { EXT_NONE = 0, EXT_X, EXT_SEG, EXT_FLOW, EXT_OUT };
 struct Op {
   OpKind kind;
   GemmPlan gemm;
+  DwconvPlan dw;
+  bool dw_tma = false;
   // generic arguments (meaning depends on kind)
   const void* src = nullptr;
   const void* src2 = nullptr;
@@ -415,6 +417,10 @@ struct Builder {
   }
   void dwconv(const bf16* x, size_t w, size_t b, int B, int H, int W, int C, bf16* out) {
     Op op; op.kind = OP_DWCONV; op.src = x; op.p0 = F(w); op.p1 = F(b); op.dst = out; op.i[0] = B; op.i[1] = H; op.i[2] = W; op.i[3] = C;
+    if (!dry() && status == SV_OK && dwconv_tma_supported(C)) {
+      op.dw_tma = true;
+      status = dwconv_tma_plan(x, F(w), F(b), B, H, W, C, out, &op.dw);
+    }
     push(op);
   }
   void attn(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads, int Nq, int Nkv, int hd) {
@@ -648,6 +654,7 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
         break;
       }
       case OP_DWCONV:
+        if (op.dw_tma) { rc = dwconv_tma_launch(op.dw, st); break; }
         rc = launch_dwconv3x3_gelu(static_cast<const bf16*>(op.src), op.p0, op.p1, op.i[0], op.i[1], op.i[2], op.i[3], static_cast<bf16*>(op.dst), st);
         break;
       case OP_ATTN:

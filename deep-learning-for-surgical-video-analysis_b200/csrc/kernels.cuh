@@ -17,6 +17,18 @@ int launch_copy_bf16_strided(const bf16* x, int64_t rows, int C, bf16* out, int6
 int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B,
                      int heads, int Nq, int Nkv, int hd, float scale, cudaStream_t st);
 
+// TMA-staged persistent depthwise conv (dwconv_tma.cu); the plan owns the tensor map of the input
+struct DwconvPlan {
+  CUtensorMap tmap;
+  const float* w9c = nullptr;
+  const float* bias = nullptr;
+  bf16* out = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+};
+bool dwconv_tma_supported(int C);
+int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, DwconvPlan* plan);
+int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st);
+
 inline int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 
 }  // namespace sv

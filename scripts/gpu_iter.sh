@@ -7,7 +7,7 @@ run kern python -m pytest tests/test_kernels_gpu.py -q -x || exit 1
 TAILN=25 run evp python -m pytest tests/test_evp_gpu.py -q -s -x || exit 1
 run mstcn python -m pytest tests/test_mstcn_gpu.py -q -x || exit 1
 for mb in ${MBS:-200}; do
-  SURGVID_PROFILE_CSV=gpurun_out/profile_ops_mb$mb.csv timeout 600 python bench.py --steps 2 --warmup 3 --micro-batch $mb --batch ${BATCH:-200} --no-e2e --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2> gpurun_out/bench_mb$mb.err
+  SURGVID_PROFILE_CSV=gpurun_out/profile_ops_mb$mb.csv timeout 600 python bench.py --steps 2 --warmup 3 --micro-batch $mb --batch $( [ "${BATCH_EQ_MB:-0}" = "1" ] && echo $mb || echo ${BATCH:-200} ) --no-e2e --no-cpu-baseline > gpurun_out/bench_mb$mb.json 2> gpurun_out/bench_mb$mb.err
   echo "bench mb=$mb rc=$?"; tail -c 300 gpurun_out/bench_mb$mb.err
   python - <<PY
 import json
