@@ -28,6 +28,7 @@ struct DwParams {
   const float* bias;
   bf16* out;
   int B, H, W, C;
+  long long ldo;
   int tiles_x, tiles_y, cblks;
   long long num_tiles;
 };
@@ -112,7 +113,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       f32x2 ring[3][3][2];
       load_row(0, ring[0]);
       load_row(1, ring[1]);
-      bf16* obase = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.C + c0;
+      bf16* obase = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.ldo + c0;
       const bool col_ok = w < p.W;
 #pragma unroll
       for (int i = 0; i < kTH; ++i) {
@@ -135,7 +136,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
           uint2 o;
           o.x = pack_bf16x2(y0, y1);
           o.y = pack_bf16x2(y2, y3);
-          *reinterpret_cast<uint2*>(obase + static_cast<long long>(i) * p.W * p.C) = o;
+          *reinterpret_cast<uint2*>(obase + static_cast<long long>(i) * p.W * p.ldo) = o;
         }
       }
       __syncwarp();
@@ -165,7 +166,8 @@ EncodeTiledFn encode_fn() {
 
 bool dwconv_tma_supported(int C) { return C % kCB == 0; }
 
-int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, DwconvPlan* plan) {
+int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo, DwconvPlan* plan) {
+  SV_CHECK(ldo >= C && ldo % 4 == 0, "dwconv output row stride");
   SV_CHECK(dwconv_tma_supported(C), "dwconv TMA path needs C % 128 == 0");
   SV_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "dwconv alignment");
   EncodeTiledFn fn = encode_fn();
@@ -177,7 +179,7 @@ int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, i
   CUresult r = fn(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(dwconv) failed, CUresult " + std::to_string(static_cast<int>(r)));
-  plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C;
+  plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C; plan->ldo = ldo;
   return SV_OK;
 }
 
@@ -188,7 +190,7 @@ int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dwconv3x3_gelu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); });
   if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(attr_err));
   DwParams p;
-  p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C;
+  p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tiles_x = ceil_div(plan.W, kTW); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
   p.num_tiles = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
   const int sms = device_sm_count();

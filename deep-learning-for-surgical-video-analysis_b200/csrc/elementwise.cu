@@ -13,7 +13,8 @@ namespace {
 template <int LPR, int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, int64_t rows, int C,
-                                                         float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+                                                         float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
+                                                         bf16* __restrict__ out_patch, int pH, int pW, int psr) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
@@ -49,6 +50,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
   if (!row_ok) return;
+  // optional second bf16 copy in "sr-patch" order: token (b,h,w) -> row (b, h/sr, w/sr), column ((h%sr)*sr + w%sr)*C + c,
+  // i.e. the A operand of the spatial-reduction conv (k = stride = sr, no padding) as a plain GEMM.
+  int64_t patch_off = -1;
+  if (out_patch != nullptr) {
+    const int w = static_cast<int>(row % pW);
+    const int h = static_cast<int>((row / pW) % pH);
+    const int64_t b = row / (static_cast<int64_t>(pW) * pH);
+    const int Hk = pH / psr, Wk = pW / psr;
+    if (h < Hk * psr && w < Wk * psr)
+      patch_off = ((b * Hk + h / psr) * Wk + w / psr) * (static_cast<int64_t>(psr) * psr * C) + ((h % psr) * psr + (w % psr)) * C;
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = sub + i * LPR;
@@ -61,22 +73,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       y.z = (v[i].z - mean) * rstd * g.z + b.z;
       y.w = (v[i].w - mean) * rstd * g.w + b.w;
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + vi * 4) = y;
-      if (out_bf16) {
+      if (out_bf16 != nullptr || patch_off >= 0) {
         uint2 o;
         o.x = pack_bf16x2(y.x, y.y);
         o.y = pack_bf16x2(y.z, y.w);
-        *reinterpret_cast<uint2*>(out_bf16 + row * C + vi * 4) = o;
+        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + row * C + vi * 4) = o;
+        if (patch_off >= 0) *reinterpret_cast<uint2*>(out_patch + patch_off + vi * 4) = o;
       }
     }
   }
 }
 
 template <int LPR, int NV>
-int ln_launch(const float* x, const float* g, const float* b, float eps, int64_t rows, int C, float* of, bf16* ob, cudaStream_t st) {
+int ln_launch(const float* x, const float* g, const float* b, float eps, int64_t rows, int C, float* of, bf16* ob, bf16* op, int pH, int pW,
+              int psr, cudaStream_t st) {
   constexpr int RPW = 32 / LPR;
   const int64_t warps = ceil_div64(rows, RPW);
   const int64_t blocks = ceil_div64(warps, 8);
-  layernorm_kernel<LPR, NV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, rows, C, of, ob);
+  layernorm_kernel<LPR, NV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, rows, C, of, ob, op, pH, pW, psr);
   return launch_status("layernorm_kernel");
 }
 
@@ -179,7 +193,7 @@ __device__ __forceinline__ void dw_load_row(DwRow& r, const bf16* __restrict__ b
 
 __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __restrict__ x, const float* __restrict__ w9c,
                                                                 const float* __restrict__ bias, int B, int H, int W, int C,
-                                                                bf16* __restrict__ out) {
+                                                                bf16* __restrict__ out, int64_t ldo) {
   const int hsegs = (H + kDwRun - 1) / kDwRun;
   const int c0 = (blockIdx.z * 32 + threadIdx.x) * 4;
   const int w = blockIdx.x * kDwCols + threadIdx.y;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
   const float4 bs = __ldg(reinterpret_cast<const float4*>(bias + c0));
   const f32x2 bias0 = f2_pack(bs.x, bs.y), bias1 = f2_pack(bs.z, bs.w);
   const bf16* base = x + static_cast<int64_t>(b) * H * W * C + c0;
-  bf16* obase = out + (static_cast<int64_t>(b) * H * W + w) * C + c0;
+  bf16* obase = out + (static_cast<int64_t>(b) * H * W + w) * ldo + c0;
   const int h0 = hs * kDwRun;
   const bool lok = w > 0, rok = w + 1 < W;
   DwRow ring[4];
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
       uint2 o;
       o.x = pack_bf16x2(y0, y1);
       o.y = pack_bf16x2(y2, y3);
-      *reinterpret_cast<uint2*>(obase + static_cast<int64_t>(h) * W * C) = o;
+      *reinterpret_cast<uint2*>(obase + static_cast<int64_t>(h) * W * ldo) = o;
     }
   }
 }
@@ -235,26 +249,38 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
 // ------------------------------------------------------------------------------------------ Gaussian 5x5 (reflect pad 2)
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
+// one thread = 4 horizontally adjacent outputs: 5 rows x 8 taps loaded once (10 loads per output instead of 25)
 __global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int H, int W) {
-  const int64_t total = static_cast<int64_t>(planes) * H * W;
+  const int wq = (W + 3) >> 2;
+  const int64_t total = static_cast<int64_t>(planes) * H * wq;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int w = static_cast<int>(idx % W);
-  const int h = static_cast<int>((idx / W) % H);
-  const int64_t pl = idx / (static_cast<int64_t>(W) * H);
+  const int w0 = static_cast<int>(idx % wq) * 4;
+  const int h = static_cast<int>((idx / wq) % H);
+  const int64_t pl = idx / (static_cast<int64_t>(wq) * H);
   const float* src = x + pl * H * W;
-  const float k1[5] = {1.f, 4.f, 6.f, 4.f, 1.f};
-  float acc = 0.f;
+  const float k1[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};  // outer(k1,k1) == [1 4 6 4 1]^2 / 256 exactly
+  int cols[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) cols[j] = reflect_idx(min(w0 + j - 2, W + 1), W);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int dy = 0; dy < 5; ++dy) {
-    const int hh = reflect_idx(h + dy - 2, H);
+    const float* rowp = src + static_cast<int64_t>(reflect_idx(h + dy - 2, H)) * W;
+    float v[8];
 #pragma unroll
-    for (int dx = 0; dx < 5; ++dx) {
-      const int ww = reflect_idx(w + dx - 2, W);
-      acc = fmaf(__ldg(src + static_cast<int64_t>(hh) * W + ww), k1[dy] * k1[dx] * (1.0f / 256.0f), acc);
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(rowp + cols[j]);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float r = 0.f;
+#pragma unroll
+      for (int dx = 0; dx < 5; ++dx) r = fmaf(v[o + dx], k1[dx], r);
+      acc[o] = fmaf(r, k1[dy], acc[o]);
     }
   }
-  out[idx] = acc;
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+    if (w0 + o < W) out[(pl * H + h) * W + w0 + o] = acc[o];
 }
 
 // ------------------------------------------------------------------------------------------ bilinear resize (align_corners=False)
@@ -329,18 +355,26 @@ inline unsigned blocks_for(int64_t total) { return static_cast<unsigned>(ceil_di
 
 }  // namespace
 
-int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
-                     bf16* out_bf16, cudaStream_t st) {
+int launch_layernorm_patch(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                           bf16* out_bf16, bf16* out_patch, int pH, int pW, int psr, cudaStream_t st) {
   SV_CHECK(C % 4 == 0 && C >= 4 && C <= 512, "layernorm supports C%4==0, C<=512");
   SV_CHECK(rows > 0, "layernorm rows");
+  if (out_patch) SV_CHECK(pH > 0 && pW > 0 && psr > 0 && rows % (static_cast<int64_t>(pH) * pW) == 0, "layernorm patch geometry");
   const int nvec = C / 4;
-  if (nvec <= 4) return ln_launch<4, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  if (nvec <= 8) return ln_launch<8, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  if (nvec <= 16) return ln_launch<16, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  if (nvec <= 32) return ln_launch<32, 1>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  if (nvec <= 64) return ln_launch<32, 2>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  if (nvec <= 96) return ln_launch<32, 3>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
-  return ln_launch<32, 4>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, st);
+#define SV_LN(L, N) return ln_launch<L, N>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, out_patch, pH, pW, psr, st)
+  if (nvec <= 4) SV_LN(4, 1);
+  if (nvec <= 8) SV_LN(8, 1);
+  if (nvec <= 16) SV_LN(16, 1);
+  if (nvec <= 32) SV_LN(32, 1);
+  if (nvec <= 64) SV_LN(32, 2);
+  if (nvec <= 96) SV_LN(32, 3);
+  SV_LN(32, 4);
+#undef SV_LN
+}
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                     bf16* out_bf16, cudaStream_t st) {
+  return launch_layernorm_patch(x, gamma, beta, eps, rows, C, out_f32, out_bf16, nullptr, 0, 0, 0, st);
 }
 
 int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, int Cin, int H, int W, int k, int stride, int pad,
@@ -362,10 +396,12 @@ int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, i
   return launch_status("im2col_nhwc_kernel");
 }
 
-int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st) {
+int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo,
+                          cudaStream_t st) {
+  SV_CHECK(ldo >= C && ldo % 4 == 0, "dwconv output row stride");
   if (dwconv_tma_supported(C)) {  // main path: TMA halo staging (dwconv_tma.cu); the register-window kernel below covers C % 128 != 0
     DwconvPlan plan;
-    SV_TRY(dwconv_tma_plan(x, w9c, bias, B, H, W, C, out, &plan));
+    SV_TRY(dwconv_tma_plan(x, w9c, bias, B, H, W, C, out, ldo, &plan));
     return dwconv_tma_launch(plan, st);
   }
   SV_CHECK(C % 4 == 0, "dwconv needs C%4==0");
@@ -373,13 +409,13 @@ int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, in
   SV_CHECK(static_cast<int64_t>(B) * hsegs <= 65535 && ceil_div(C, 128) <= 65535, "dwconv grid limits");
   dim3 grid(ceil_div(W, kDwCols), B * hsegs, ceil_div(C, 128));
   dim3 block(32, kDwCols);
-  dwconv3x3_gelu_kernel<<<grid, block, 0, st>>>(x, w9c, bias, B, H, W, C, out);
+  dwconv3x3_gelu_kernel<<<grid, block, 0, st>>>(x, w9c, bias, B, H, W, C, out, ldo);
   return launch_status("dwconv3x3_gelu_kernel");
 }
 
 int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st) {
   SV_CHECK(H >= 3 && W >= 3, "gauss5x5 needs H,W >= 3 (reflect pad 2)");
-  gauss5x5_kernel<<<blocks_for(static_cast<int64_t>(planes) * H * W), 256, 0, st>>>(x, out, planes, H, W);
+  gauss5x5_kernel<<<blocks_for(static_cast<int64_t>(planes) * H * ((W + 3) / 4)), 256, 0, st>>>(x, out, planes, H, W);
   return launch_status("gauss5x5_kernel");
 }
 
@@ -420,7 +456,7 @@ int sv_op_im2col(const float* src_nchw_f32, const uint16_t* src_nhwc_bf16, int32
 }
 int sv_op_dwconv3x3_gelu(const uint16_t* x, const float* w, const float* bias, int32_t B, int32_t H, int32_t W, int32_t C, uint16_t* out,
                          void* stream) {
-  return sv::launch_dwconv3x3_gelu(reinterpret_cast<const sv::bf16*>(x), w, bias, B, H, W, C, reinterpret_cast<sv::bf16*>(out),
+  return sv::launch_dwconv3x3_gelu(reinterpret_cast<const sv::bf16*>(x), w, bias, B, H, W, C, reinterpret_cast<sv::bf16*>(out), C,
                                    static_cast<cudaStream_t>(stream));
 }
 int sv_op_gauss5x5(const float* x, float* out, int32_t planes, int32_t H, int32_t W, void* stream) {

@@ -42,6 +42,7 @@ struct Norm {       // LayerNorm affine, fp32
 struct BlockW {
   Norm n1, n2, srn;
   Lin q, kv, proj, sr, fc1, fc2;
+  Lin fc2cat;  // [fc2 | shared_mlp] along K: x += fc2(h) + shared_mlp(T_next) in one GEMM (blocks that have a successor)
   size_t dw_w = 0, dw_b = 0;  // fp32 [9][4C], [4C]
 };
 struct StageW {
@@ -69,6 +70,7 @@ struct Op {
   const void* src3 = nullptr;
   void* dst = nullptr;
   void* dst2 = nullptr;
+  void* dst3 = nullptr;
   const float* p0 = nullptr;
   const float* p1 = nullptr;
   int64_t l0 = 0, l1 = 0, l2 = 0, l3 = 0;
@@ -273,6 +275,26 @@ int pack_all(sv_evp* h) {
       B.dw_b = P.vec(bp + ".mlp.dwconv.dwconv.bias", hid);
       S.blk.push_back(B);
     }
+    // Adapter fusion: the adapter term of block i+1, shared_mlp(GELU(lightweight_mlp_{i+1}(P))), does not depend on x, so it
+    // is added by block i's fc2 GEMM: K-concatenated weight [W_fc2_i | W_shared], bias b_fc2_i + b_shared.
+    {
+      const HostTensor* wsh = P.get("prompt_generator.shared_mlp" + sn + ".weight", {C, Cp});
+      const HostTensor* bsh = P.get("prompt_generator.shared_mlp" + sn + ".bias", {C});
+      for (int i = 0; i + 1 < c.depths[s] && wsh && bsh; ++i) {
+        const std::string bp = "block" + sn + "." + std::to_string(i);
+        const HostTensor* w2 = P.get(bp + ".mlp.fc2.weight", {C, hid});
+        const HostTensor* b2 = P.get(bp + ".mlp.fc2.bias", {C});
+        if (!w2 || !b2) break;
+        std::vector<float> wc(static_cast<size_t>(C) * (hid + Cp)), bc(C);
+        for (int n = 0; n < C; ++n) {
+          std::copy(w2->data.begin() + static_cast<size_t>(n) * hid, w2->data.begin() + static_cast<size_t>(n + 1) * hid, wc.begin() + static_cast<size_t>(n) * (hid + Cp));
+          std::copy(wsh->data.begin() + static_cast<size_t>(n) * Cp, wsh->data.begin() + static_cast<size_t>(n + 1) * Cp,
+                    wc.begin() + static_cast<size_t>(n) * (hid + Cp) + hid);
+          bc[n] = b2->data[n] + bsh->data[n];
+        }
+        S.blk[i].fc2cat = P.linear_raw(wc.data(), bc.data(), C, hid + Cp);
+      }
+    }
     S.norm = P.norm("norm" + sn, C);
   }
   // flow encoder: conv + BN(eval) folded, ReLU applied in the GEMM epilogue
@@ -406,8 +428,9 @@ struct Builder {
     plan->gemm_flops += op.gemm.flops;
     push(op);
   }
-  void ln(const float* x, const Norm& n, float eps, int64_t rows, float* of, bf16* ob) {
+  void ln(const float* x, const Norm& n, float eps, int64_t rows, float* of, bf16* ob, bf16* patch = nullptr, int pH = 0, int pW = 0, int psr = 0) {
     Op op; op.kind = OP_LN; op.src = x; op.p0 = F(n.g); op.p1 = F(n.b); op.f0 = eps; op.l0 = rows; op.i[0] = n.C; op.dst = of; op.dst2 = ob;
+    op.dst3 = patch; op.i[1] = pH; op.i[2] = pW; op.i[3] = psr;
     push(op);
   }
   void im2col(const float* nchw, const bf16* nhwc, int B, int Cin, int H, int W, int k, int stride, int pad, bf16* out, int64_t ldo, int ext = EXT_NONE) {
@@ -415,11 +438,12 @@ struct Builder {
     op.i[0] = B; op.i[1] = Cin; op.i[2] = H; op.i[3] = W; op.i[4] = k; op.i[5] = stride; op.i[6] = pad;
     push(op);
   }
-  void dwconv(const bf16* x, size_t w, size_t b, int B, int H, int W, int C, bf16* out) {
+  void dwconv(const bf16* x, size_t w, size_t b, int B, int H, int W, int C, bf16* out, int64_t ldo) {
     Op op; op.kind = OP_DWCONV; op.src = x; op.p0 = F(w); op.p1 = F(b); op.dst = out; op.i[0] = B; op.i[1] = H; op.i[2] = W; op.i[3] = C;
+    op.l0 = ldo;
     if (!dry() && status == SV_OK && dwconv_tma_supported(C)) {
       op.dw_tma = true;
-      status = dwconv_tma_plan(x, F(w), F(b), B, H, W, C, out, &op.dw);
+      status = dwconv_tma_plan(x, F(w), F(b), B, H, W, C, out, ldo, &op.dw);
     }
     push(op);
   }
@@ -457,12 +481,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   const int ks[4] = {7, 3, 3, 3}, strd[4] = {4, 2, 2, 2};
 
   // ---- sizes of stage-scoped buffers (max over stages)
-  size_t max_tok_c = 0, max_tok_cp = 0, max_tok_hid = 0, max_kv_c = 0, max_sr_k = 0, max_col = 0, max_conv_out = 0;
+  size_t max_tok_c = 0, max_tok_cp = 0, max_tok_hid = 0, max_tok_hidcat = 0, max_kv_c = 0, max_sr_k = 0, max_col = 0, max_conv_out = 0;
   for (int s = 0; s < 4; ++s) {
     const size_t M = static_cast<size_t>(n) * g[s].N, Mk = static_cast<size_t>(n) * g[s].Nkv;
     max_tok_c = std::max(max_tok_c, M * g[s].C);
     max_tok_cp = std::max(max_tok_cp, M * g[s].Cp);
     max_tok_hid = std::max(max_tok_hid, M * g[s].hidden);
+    max_tok_hidcat = std::max(max_tok_hidcat, M * (g[s].hidden + g[s].Cp));
     max_kv_c = std::max(max_kv_c, Mk * g[s].C);
     if (g[s].sr > 1) max_sr_k = std::max(max_sr_k, Mk * static_cast<size_t>(g[s].sr * g[s].sr * g[s].C));
     const int cin = s == 0 ? 3 : c.embed_dims[s - 1];
@@ -501,7 +526,7 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   bf16* srn = A.get<bf16>(max_kv_c);
   bf16* kvb = A.get<bf16>(2 * max_kv_c);
   bf16* h1 = A.get<bf16>(max_tok_hid);
-  bf16* h2 = A.get<bf16>(max_tok_hid);
+  bf16* h2 = A.get<bf16>(max_tok_hidcat);  // [M, 4C + C/4]: GELU(dwconv(h1)) | adapter T of the NEXT block
 
   // ---- 0. handcrafted prompts: gaussian(seg) -> 4 chained OverlapPatchEmbeds (mix_transformer_evp.py:718-747)
   b.gauss(seg_g, n * 3, H, W);
@@ -532,20 +557,26 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
       b.ln(conv_out, S.pe_norm, 1e-5f, M, x, xn);
       // init_prompt (:749-756): P = handcrafted_s + embedding_generator_s(x)   (constant over depth)
       b.gemm(xn, C, S.emb, M, ACT_NONE, hc_f32[s], G.Cp, Pb, G.Cp, 0);
+      const int ldh = G.hidden + G.Cp;
       for (int i = 0; i < c.depths[s]; ++i) {
         const BlockW& Bk = S.blk[i];
-        // get_prompt (:776-815): x += shared_mlp(GELU(lightweight_mlp_i(P)))
-        b.gemm(Pb, G.Cp, S.lw[i], M, ACT_GELU, nullptr, 0, Tb, G.Cp, 0);
-        b.gemm(Tb, G.Cp, S.shared, M, ACT_NONE, x, C, x, C, 1);
-        // attention (:110-131)
-        b.ln(x, Bk.n1, 1e-6f, M, nullptr, xn);
-        b.gemm(xn, C, Bk.q, M, ACT_NONE, nullptr, 0, qb, C, 0);
+        const bool has_next = i + 1 < c.depths[s];
+        // get_prompt (:776-815): x += shared_mlp(GELU(lightweight_mlp_i(P))).  Only block 0 does this as its own GEMM pair;
+        // for i >= 1 the term was already added by block i-1's K-concatenated fc2 GEMM (see pack_all).
+        if (i == 0) {
+          b.gemm(Pb, G.Cp, S.lw[0], M, ACT_GELU, nullptr, 0, Tb, G.Cp, 0);
+          b.gemm(Tb, G.Cp, S.shared, M, ACT_NONE, x, C, x, C, 1);
+        }
+        // attention (:110-131); LN1 also emits the sr-conv's A operand (non-overlapping sr x sr patches) directly
         if (G.sr > 1) {
-          b.im2col(nullptr, xn, n, C, G.H, G.W, G.sr, G.sr, 0, a_sr, Bk.sr.ldw);
+          b.ln(x, Bk.n1, 1e-6f, M, nullptr, xn, a_sr, G.H, G.W, G.sr);
+          b.gemm(xn, C, Bk.q, M, ACT_NONE, nullptr, 0, qb, C, 0);
           b.gemm(a_sr, Bk.sr.ldw, Bk.sr, Mk, ACT_NONE, nullptr, 0, sr_out, C, 1);
           b.ln(sr_out, Bk.srn, 1e-5f, Mk, nullptr, srn);
           b.gemm(srn, C, Bk.kv, Mk, ACT_NONE, nullptr, 0, kvb, 2 * C, 0);
         } else {
+          b.ln(x, Bk.n1, 1e-6f, M, nullptr, xn);
+          b.gemm(xn, C, Bk.q, M, ACT_NONE, nullptr, 0, qb, C, 0);
           b.gemm(xn, C, Bk.kv, M, ACT_NONE, nullptr, 0, kvb, 2 * C, 0);
         }
         b.attn(qb, C, kvb, 2 * C, kvb + C, 2 * C, ob, C, n, G.heads, G.N, G.Nkv, C / G.heads);
@@ -553,8 +584,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
         // MixFFN (:60-67)
         b.ln(x, Bk.n2, 1e-6f, M, nullptr, xn);
         b.gemm(xn, C, Bk.fc1, M, ACT_NONE, nullptr, 0, h1, G.hidden, 0);
-        b.dwconv(h1, Bk.dw_w, Bk.dw_b, n, G.H, G.W, G.hidden, h2);
-        b.gemm(h2, G.hidden, Bk.fc2, M, ACT_NONE, x, C, x, C, 1);
+        b.dwconv(h1, Bk.dw_w, Bk.dw_b, n, G.H, G.W, G.hidden, h2, ldh);
+        if (has_next) {
+          b.gemm(Pb, G.Cp, S.lw[i + 1], M, ACT_GELU, nullptr, 0, h2 + G.hidden, ldh, 0);   // T_{i+1} into the K tail of h2
+          b.gemm(h2, ldh, Bk.fc2cat, M, ACT_NONE, x, C, x, C, 1);                           // x += fc2(h) + shared_mlp(T_{i+1})
+        } else {
+          b.gemm(h2, ldh, Bk.fc2, M, ACT_NONE, x, C, x, C, 1);
+        }
       }
       b.ln(x, S.norm, 1e-6f, M, c_f32[s], c_b16[s]);
       b.tap("stage" + std::to_string(s + 1) + "_tokens", c_b16[s], static_cast<int64_t>(M) * C);
@@ -642,8 +678,8 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
     switch (op.kind) {
       case OP_GEMM: rc = gemm_launch(op.gemm, st); break;
       case OP_LN:
-        rc = launch_layernorm(static_cast<const float*>(op.src), op.p0, op.p1, op.f0, op.l0, op.i[0], static_cast<float*>(op.dst),
-                              static_cast<bf16*>(op.dst2), st);
+        rc = launch_layernorm_patch(static_cast<const float*>(op.src), op.p0, op.p1, op.f0, op.l0, op.i[0], static_cast<float*>(op.dst),
+                                    static_cast<bf16*>(op.dst2), static_cast<bf16*>(op.dst3), op.i[1], op.i[2], op.i[3], st);
         break;
       case OP_IM2COL: {
         const float* nchw = static_cast<const float*>(op.src);
@@ -655,7 +691,7 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
       }
       case OP_DWCONV:
         if (op.dw_tma) { rc = dwconv_tma_launch(op.dw, st); break; }
-        rc = launch_dwconv3x3_gelu(static_cast<const bf16*>(op.src), op.p0, op.p1, op.i[0], op.i[1], op.i[2], op.i[3], static_cast<bf16*>(op.dst), st);
+        rc = launch_dwconv3x3_gelu(static_cast<const bf16*>(op.src), op.p0, op.p1, op.i[0], op.i[1], op.i[2], op.i[3], static_cast<bf16*>(op.dst), op.l0, st);
         break;
       case OP_ATTN:
         rc = launch_attention(static_cast<const bf16*>(op.src), op.l0, static_cast<const bf16*>(op.src2), op.l1, static_cast<const bf16*>(op.src3),

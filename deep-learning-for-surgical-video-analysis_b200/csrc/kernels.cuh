@@ -6,9 +6,12 @@ namespace sv {
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
                      bf16* out_bf16, cudaStream_t st);
+int launch_layernorm_patch(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                           bf16* out_bf16, bf16* out_patch, int pH, int pW, int psr, cudaStream_t st);
 int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, int Cin, int H, int W, int k, int stride, int pad,
                   bf16* out, int64_t ldo, cudaStream_t st);
-int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, cudaStream_t st);
+int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo,
+                          cudaStream_t st);
 int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st);
 int launch_bilinear_tokens(const bf16* x, int B, int H, int W, int C, int Ho, int Wo, bf16* out, int64_t ldo, cudaStream_t st);
 int launch_token_mean(const float* x, int B, int tokens, int C, float* out, cudaStream_t st);
@@ -24,9 +27,10 @@ struct DwconvPlan {
   const float* bias = nullptr;
   bf16* out = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
+  int64_t ldo = 0;  // output row (pixel) stride in elements, >= C
 };
 bool dwconv_tma_supported(int C);
-int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, DwconvPlan* plan);
+int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo, DwconvPlan* plan);
 int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st);
 
 inline int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
