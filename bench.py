@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FRAMES_PER_VIDEO = 2300
-BATCH = 200
+BATCH = 800  # throughput-optimal on B200; the reference driver uses 200 (generate_evp_LFB.py:36), see DESIGN.md for both
 FLOPS_PER_FRAME_REF = 16.664e9  # reference graph @224^2 with flow
 
 
@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_VIDEO)
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("SURGVID_MICRO_BATCH", "32")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("SURGVID_MICRO_BATCH", "800")))
     ap.add_argument("--fold-head", type=int, default=int(os.environ.get("SURGVID_FOLD_HEAD", "0")))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

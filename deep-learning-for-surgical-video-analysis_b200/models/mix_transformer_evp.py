@@ -197,7 +197,7 @@ class MixVisionTransformerEVP(nn.Module):
         self.cross_attn_s4 = MotionGuidedCrossAttention(dim=embed_dims[3])
         # ---- native state (not parameters, not in state_dict)
         self.embedding_dim = self.head.embedding_dim
-        self.micro_batch = int(os.environ.get("SURGVID_MICRO_BATCH", "32"))
+        self.micro_batch = int(os.environ.get("SURGVID_MICRO_BATCH", "800"))
         self.fold_head = bool(int(os.environ.get("SURGVID_FOLD_HEAD", "0")))
         self._native = {}  # device index -> dict(handle, stamp, workspace)
 
