@@ -184,11 +184,169 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   }
 }
 
+// ---- N_kv <= 64 (every encoder block at 224x224: N_kv = 49): K and V of one (frame, head) stay resident in shared memory
+// while the CTA walks over several 64-row query tiles; query tiles are double-buffered with cp.async, the softmax is single
+// pass (all keys at once), and the output tile goes back through shared memory so that global stores are 16-byte coalesced.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;  // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HD>
+__device__ __forceinline__ void load_tile_async(bf16* __restrict__ dst, const bf16* __restrict__ src, int64_t ld, int r0, int rows_total) {
+  using S = AttnShape<HD>;
+  constexpr int CH = S::HDP / 8;
+  for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+    const int r = i / CH, c = i % CH;
+    const bool ok = (r0 + r < rows_total) && (c * 8 < HD);
+    const bf16* g = ok ? src + static_cast<int64_t>(r0 + r) * ld + c * 8 : src;
+    cp_async16(dst + r * S::LDS + c * 8, g, ok);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_resident_kv_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
+                                                                    const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
+                                                                    int Nq, int Nkv, float scale_log2, int tiles_per_cta) {
+  using S = AttnShape<HD>;
+  __shared__ __align__(16) bf16 Qs[2][kTile * S::LDS];
+  __shared__ __align__(16) bf16 Ks[kTile * S::LDS];
+  __shared__ __align__(16) bf16 Vs[kTile * S::LDS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int ntiles = min(tiles_per_cta, (Nq + kTile - 1) / kTile - tile0);
+  const bf16* qb = q + static_cast<int64_t>(b) * Nq * ldq + head * HD;
+  const bf16* kb = k + static_cast<int64_t>(b) * Nkv * ldk + head * HD;
+  const bf16* vb = v + static_cast<int64_t>(b) * Nkv * ldv + head * HD;
+  bf16* ob = o + static_cast<int64_t>(b) * Nq * ldo + head * HD;
+
+  load_tile_async<HD>(Ks, kb, ldk, 0, Nkv);
+  load_tile_async<HD>(Vs, vb, ldv, 0, Nkv);
+  load_tile_async<HD>(Qs[0], qb, ldq, tile0 * kTile, Nq);
+  cp_async_commit();
+
+  const int mi = lane >> 3;
+  for (int j = 0; j < ntiles; ++j) {
+    const int q0 = (tile0 + j) * kTile;
+    bf16* Qc = Qs[j & 1];
+    if (j + 1 < ntiles) load_tile_async<HD>(Qs[(j + 1) & 1], qb, ldq, q0 + kTile, Nq);  // overlaps this tile's math
+    cp_async_commit();
+    cp_async_wait<1>();  // everything except the group just committed has landed (K, V, Q(j))
+    __syncthreads();
+
+    uint32_t qf[S::KS][4];
+    {
+      const int row = warp * 16 + (mi & 1) * 8 + (lane & 7);
+#pragma unroll
+      for (int ks = 0; ks < S::KS; ++ks)
+        ldmatrix_x4(qf[ks], static_cast<uint32_t>(__cvta_generic_to_shared(Qc + row * S::LDS + ks * 16 + (mi >> 1) * 8)));
+    }
+    float sacc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < S::KS; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
+        uint32_t kf[4];
+        ldmatrix_x4(kf, static_cast<uint32_t>(__cvta_generic_to_shared(Ks + key * S::LDS + ks * 16 + (mi & 1) * 8)));
+        mma_bf16_16816(sacc[np * 2], qf[ks], kf[0], kf[1]);
+        mma_bf16_16816(sacc[np * 2 + 1], qf[ks], kf[2], kf[3]);
+      }
+    }
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + t * 2 + (e & 1);
+        float sv = sacc[nt][e] * scale_log2;
+        if (key >= Nkv) sv = -INFINITY;
+        sacc[nt][e] = sv;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sv);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float l[2] = {0.f, 0.f};
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f(sacc[nt][0] - mx[0]), p1 = exp2f(sacc[nt][1] - mx[0]);
+      const float p2 = exp2f(sacc[nt][2] - mx[1]), p3 = exp2f(sacc[nt][3] - mx[1]);
+      l[0] += p0 + p1;
+      l[1] += p2 + p3;
+      const int kk = nt >> 1;
+      if ((nt & 1) == 0) { pf[kk][0] = pack_bf16x2(p0, p1); pf[kk][1] = pack_bf16x2(p2, p3); }
+      else               { pf[kk][2] = pack_bf16x2(p0, p1); pf[kk][3] = pack_bf16x2(p2, p3); }
+    }
+    float oacc[S::NTO][4];
+#pragma unroll
+    for (int i = 0; i < S::NTO; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int dp = 0; dp < S::NTO / 2; ++dp) {
+        const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, static_cast<uint32_t>(__cvta_generic_to_shared(Vs + key * S::LDS + (dp * 2 + (mi >> 1)) * 8)));
+        mma_bf16_16816(oacc[dp * 2], pf[kk], vf[0], vf[1]);
+        mma_bf16_16816(oacc[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+    // this warp's 16 output rows go back through its own rows of the (now consumed) query tile, then out 16 bytes per lane
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < S::NTO; ++i) {
+      const int col = i * 8 + t * 2;
+      *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g) * S::LDS + col) = pack_bf16x2(oacc[i][0] * inv0, oacc[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g + 8) * S::LDS + col) = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
+    }
+    __syncwarp();
+    constexpr int CH = HD / 8;  // 16-byte chunks per output row
+    for (int i = lane; i < 16 * CH; i += 32) {
+      const int r = i / CH, c = i % CH;
+      const int row = q0 + warp * 16 + r;
+      if (row < Nq)
+        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+    }
+    __syncthreads();  // Qc may be refilled by the prefetch issued at the top of the next-but-one iteration
+  }
+  cp_async_wait<0>();
+}
+
 template <int HD>
 int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads,
                 int Nq, int Nkv, float scale, cudaStream_t st) {
-  dim3 grid(ceil_div(Nq, kTile), heads, B);
-  attention_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale * 1.4426950408889634f);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  const int qtiles = ceil_div(Nq, kTile);
+  if (Nkv <= kTile && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    // enough CTAs to fill the machine a few times over, but as many query tiles per CTA as that allows (K/V loaded once per CTA)
+    int tpc = 1;
+    while (tpc < 8 && tpc < qtiles && static_cast<long long>(ceil_div(qtiles, tpc * 2)) * heads * B >= 4LL * 148 * 4) tpc *= 2;
+    if (qtiles <= 4) tpc = qtiles;
+    dim3 grid(ceil_div(qtiles, tpc), heads, B);
+    attention_resident_kv_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2, tpc);
+    return launch_status("attention_resident_kv_kernel");
+  }
+  dim3 grid(qtiles, heads, B);
+  attention_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2);
   return launch_status("attention_kernel");
 }
 

@@ -38,6 +38,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ int4 tile_coord[kStages];  // (cblk, tx, ty, b) of the tile in each stage, written by the producer
   uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -65,6 +66,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
         const int ty = static_cast<int>(r % p.tiles_y);
         const int b = static_cast<int>(r / p.tiles_y);
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        tile_coord[stage] = make_int4(cblk, tx, ty, b);  // visible to the consumers through the barrier's release/acquire
         ptx::mbar_arrive_expect_tx(&full_bar[stage], kTileBytes);
         ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * kTW - 1, ty * kTH - 1, b);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -79,11 +81,9 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
     f32x2 wt[9][2];
     f32x2 bias0 = 0, bias1 = 0;
     for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int cblk = static_cast<int>(t / tiles_per_cblk);
-      long long r = t % tiles_per_cblk;
-      const int tx = static_cast<int>(r % p.tiles_x); r /= p.tiles_x;
-      const int ty = static_cast<int>(r % p.tiles_y);
-      const int b = static_cast<int>(r / p.tiles_y);
+      ptx::mbar_wait(&full_bar[stage], phase);
+      const int4 tc = tile_coord[stage];
+      const int cblk = tc.x, tx = tc.y, ty = tc.z, b = tc.w;
       const int c0 = cblk * kCB + lane * 4;
       if (cblk != cur_cblk) {  // weights of this 128-channel block stay in registers across tiles
         cur_cblk = cblk;
@@ -99,7 +99,6 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       }
       const int w = tx * kTW + col;
       const int h0 = ty * kTH;
-      ptx::mbar_wait(&full_bar[stage], phase);
       // smem tile: [kBoxH][kBoxW][128 ch] bf16; this thread reads box columns col, col+1, col+2
       const uint2* tile = reinterpret_cast<const uint2*>(smem + stage * kTileBytes) + col * (kCB / 4) + lane;
       auto load_row = [&](int br, f32x2 (&dst)[3][2]) {
