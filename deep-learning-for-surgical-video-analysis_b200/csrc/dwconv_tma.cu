@@ -15,7 +15,7 @@
 namespace sv {
 namespace {
 
-constexpr int kTW = 8;          // output columns per tile (= consumer warps)
+constexpr int kTW = 8;          // max output columns per tile (= consumer warps); 7 or 8 are used, whichever tiles W exactly
 constexpr int kTH = 7;          // output rows per tile
 constexpr int kCB = 128;        // channels per tile (32 lanes x 4)
 constexpr int kStages = 3;
@@ -30,6 +30,7 @@ struct DwParams {
   int B, H, W, C;
   long long ldo;
   int tiles_x, tiles_y, cblks;
+  int tw;  // output columns per tile actually used (<= kTW); box width = tw + 2
   long long num_tiles;
 };
 
@@ -46,7 +47,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
     ptx::prefetch_tensormap(&tmap_x);
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], kTW);
+      ptx::mbar_init(&empty_bar[s], p.tw);
     }
     ptx::fence_barrier_init();
   }
@@ -67,14 +68,15 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
         const int b = static_cast<int>(r / p.tiles_y);
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
         tile_coord[stage] = make_int4(cblk, tx, ty, b);  // visible to the consumers through the barrier's release/acquire
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], kTileBytes);
-        ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * kTW - 1, ty * kTH - 1, b);
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBoxH * (p.tw + 2) * kCB * 2));
+        ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * p.tw - 1, ty * kTH - 1, b);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else {
+  } else if (warp - 1 < p.tw) {
     // ------------------------------------------------------------ consumers: warp -> column, lane -> 4 channels
     const int col = warp - 1;
+    const int boxw = p.tw + 2;
     int stage = 0;
     uint32_t phase = 0;
     int cur_cblk = -1;
@@ -97,14 +99,14 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
         bias0 = f2_pack(b4.x, b4.y);
         bias1 = f2_pack(b4.z, b4.w);
       }
-      const int w = tx * kTW + col;
+      const int w = tx * p.tw + col;
       const int h0 = ty * kTH;
       // smem tile: [kBoxH][kBoxW][128 ch] bf16; this thread reads box columns col, col+1, col+2
       const uint2* tile = reinterpret_cast<const uint2*>(smem + stage * kTileBytes) + col * (kCB / 4) + lane;
       auto load_row = [&](int br, f32x2 (&dst)[3][2]) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const uint2 v = tile[(br * kBoxW + dx) * (kCB / 4)];
+          const uint2 v = tile[(br * boxw + dx) * (kCB / 4)];
           dst[dx][0] = f2_from_bf16x2(v.x);
           dst[dx][1] = f2_from_bf16x2(v.y);
         }
@@ -173,12 +175,13 @@ int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, i
   if (!fn) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point unavailable");
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
-  cuuint32_t box[4] = {kCB, kBoxW, kBoxH, 1};
+  const int tw = (W % 8 == 0) ? 8 : ((W % 7 == 0) ? 7 : 8);
+  cuuint32_t box[4] = {kCB, static_cast<cuuint32_t>(tw + 2), kBoxH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(dwconv) failed, CUresult " + std::to_string(static_cast<int>(r)));
-  plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C; plan->ldo = ldo;
+  plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C; plan->ldo = ldo; plan->tw = tw;
   return SV_OK;
 }
 
@@ -190,7 +193,8 @@ int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(attr_err));
   DwParams p;
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
-  p.tiles_x = ceil_div(plan.W, kTW); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
+  p.tw = plan.tw;
+  p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
   p.num_tiles = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
   const int sms = device_sm_count();
   const int grid = static_cast<int>(std::min<long long>(p.num_tiles, 2LL * sms));

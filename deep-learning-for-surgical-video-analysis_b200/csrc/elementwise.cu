@@ -53,13 +53,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   // optional second bf16 copy in "sr-patch" order: token (b,h,w) -> row (b, h/sr, w/sr), column ((h%sr)*sr + w%sr)*C + c,
   // i.e. the A operand of the spatial-reduction conv (k = stride = sr, no padding) as a plain GEMM.
   int64_t patch_off = -1;
-  if (out_patch != nullptr) {
-    const int w = static_cast<int>(row % pW);
-    const int h = static_cast<int>((row / pW) % pH);
-    const int64_t b = row / (static_cast<int64_t>(pW) * pH);
-    const int Hk = pH / psr, Wk = pW / psr;
-    if (h < Hk * psr && w < Wk * psr)
-      patch_off = ((b * Hk + h / psr) * Wk + w / psr) * (static_cast<int64_t>(psr) * psr * C) + ((h % psr) * psr + (w % psr)) * C;
+  if (out_patch != nullptr) {  // 32-bit index math (rows < 2^31 checked by the launcher); sr is a power of two
+    const uint32_t r32 = static_cast<uint32_t>(row);
+    const uint32_t hw = static_cast<uint32_t>(pH) * static_cast<uint32_t>(pW);
+    const uint32_t b = r32 / hw;
+    const uint32_t rem = r32 - b * hw;
+    const uint32_t h = rem / static_cast<uint32_t>(pW);
+    const uint32_t w = rem - h * static_cast<uint32_t>(pW);
+    const uint32_t lg = 31u - __clz(psr);
+    const uint32_t Hk = static_cast<uint32_t>(pH) >> lg, Wk = static_cast<uint32_t>(pW) >> lg;
+    const uint32_t hq = h >> lg, wq = w >> lg;
+    if (hq < Hk && wq < Wk)
+      patch_off = (static_cast<int64_t>((b * Hk + hq) * Wk + wq) << (2 * lg)) * C + (((h & (psr - 1)) << lg) + (w & (psr - 1))) * C;
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -359,7 +364,9 @@ int launch_layernorm_patch(const float* x, const float* gamma, const float* beta
                            bf16* out_bf16, bf16* out_patch, int pH, int pW, int psr, cudaStream_t st) {
   SV_CHECK(C % 4 == 0 && C >= 4 && C <= 512, "layernorm supports C%4==0, C<=512");
   SV_CHECK(rows > 0, "layernorm rows");
-  if (out_patch) SV_CHECK(pH > 0 && pW > 0 && psr > 0 && rows % (static_cast<int64_t>(pH) * pW) == 0, "layernorm patch geometry");
+  if (out_patch)
+    SV_CHECK(pH > 0 && pW > 0 && psr > 0 && (psr & (psr - 1)) == 0 && rows % (static_cast<int64_t>(pH) * pW) == 0 && rows < (1LL << 31),
+             "layernorm patch geometry (sr must be a power of two)");
   const int nvec = C / 4;
 #define SV_LN(L, N) return ln_launch<L, N>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, out_patch, pH, pW, psr, st)
   if (nvec <= 4) SV_LN(4, 1);
