@@ -280,19 +280,23 @@ def run_ours(args):
             for b0 in range(0, T, B):
                 model(x[b0:min(T, b0 + B)], seg[b0:min(T, b0 + B)], flow[b0:min(T, b0 + B)], return_features=True)
         torch.cuda.synchronize()
-        ms_k = (ctypes.c_double * 8)()
-        n_k = (ctypes.c_int64 * 8)()
+        ms_k = (ctypes.c_double * 16)()
+        n_k = (ctypes.c_int64 * 16)()
         fl = ctypes.c_double(0)
-        lib.sv_evp_get_profile(h, ms_k, n_k, ctypes.byref(fl))
+        by_k = (ctypes.c_double * 16)()
+        lib.sv_evp_get_profile(h, ms_k, n_k, ctypes.byref(fl), by_k)
         if os.environ.get("SURGVID_PROFILE_CSV"):
             lib.sv_evp_dump_profile(h, os.environ["SURGVID_PROFILE_CSV"].encode())
         lib.sv_evp_set_profile(h, 0)
-        names = ["gemm_tcgen05", "layernorm", "im2col", "dwconv3x3_gelu", "attention", "gauss5x5", "bilinear", "token_mean"]
-        tot = sum(ms_k)
-        classes = {nm: {"ms_per_step": ms_k[i], "launches_per_step": int(n_k[i]), "share": (ms_k[i] / tot if tot else 0.0)} for i, nm in enumerate(names)}
-        # algorithmic bytes of the HBM-bound classes (SURVEY.md §8d, bf16 activations): DWConv+GELU 35.3 MB/frame
-        classes["dwconv3x3_gelu"]["hbm_gbs"] = 35.3e6 * T / (ms_k[3] / 1e3) / 1e9 if ms_k[3] else None
-        classes["dwconv3x3_gelu"]["hbm_frac"] = classes["dwconv3x3_gelu"]["hbm_gbs"] / peaks["hbm_gbs"] if ms_k[3] else None
+        names = ["gemm_tcgen05", "layernorm", "im2col", "dwconv3x3_gelu", "attention", "gauss5x5", "bilinear", "token_mean", "stem_conv"]
+        tot = sum(ms_k[i] for i in range(len(names)))
+        # per class: device ms, launches, share of the step, algorithmic HBM bytes (operands + results of each launch once)
+        # and the HBM bandwidth / fraction of the measured copy peak they imply
+        classes = {}
+        for i, nm in enumerate(names):
+            gbs = by_k[i] / (ms_k[i] / 1e3) / 1e9 if ms_k[i] else None
+            classes[nm] = {"ms_per_step": ms_k[i], "launches_per_step": int(n_k[i]), "share": (ms_k[i] / tot if tot else 0.0),
+                           "alg_mbytes_per_frame": by_k[i] / T / 1e6, "hbm_gbs": gbs, "hbm_frac": (gbs / peaks["hbm_gbs"] if gbs else None)}
         gemm_ms_per_launch = ms_k[0] / max(1, n_k[0])
         achieved = fl.value / (ms_k[0] / 1e3) / 1e12 if ms_k[0] else 0.0
         roofline = {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],

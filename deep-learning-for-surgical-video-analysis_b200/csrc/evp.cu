@@ -56,7 +56,7 @@ struct CrossW {
   Norm norm;
 };
 
-enum OpKind { OP_GEMM, OP_LN, OP_IM2COL, OP_DWCONV, OP_ATTN, OP_GAUSS, OP_BILINEAR, OP_MEAN };
+enum OpKind { OP_GEMM, OP_LN, OP_IM2COL, OP_DWCONV, OP_ATTN, OP_GAUSS, OP_BILINEAR, OP_MEAN, OP_STEM, OP_KINDS };
 enum Ext { EXT_NONE = 0, EXT_X, EXT_SEG, EXT_FLOW, EXT_OUT };
 
 struct Op {
@@ -77,6 +77,7 @@ struct Op {
   int i[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   float f0 = 0.f;
   int ext_src = EXT_NONE, ext_dst = EXT_NONE;
+  double alg_bytes = 0.0;         // algorithmic HBM bytes of this launch (operands + results once)
   mutable double prof_ms = 0.0;   // filled only in profiling mode
   mutable long long prof_n = 0;
 };
@@ -93,6 +94,7 @@ struct Plan {
   std::vector<Op> ops;
   std::map<std::string, Tap> taps;
   double gemm_flops = 0.0;
+  double bytes_by_kind[OP_KINDS] = {};
 };
 
 // bump allocator over the caller's workspace (dry run when base == nullptr)
@@ -135,9 +137,10 @@ struct sv_evp {
   int64_t launches = 0;
   // optional per-kernel-class timing (CUDA events around every launch; bench.py's roofline pass)
   bool profile = false;
-  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t prof_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_ms[sv::OP_KINDS] = {};
+  int64_t prof_n[sv::OP_KINDS] = {};
   double prof_gemm_flops = 0.0;
+  double prof_bytes[sv::OP_KINDS] = {};
   std::vector<cudaEvent_t> prof_events;
 };
 
@@ -411,10 +414,15 @@ struct Builder {
   Builder(sv_evp* hh, Plan* p, void* ws) : h(hh), plan(p), arena(ws) {}
   bool dry() const { return plan == nullptr; }
   const bf16* W(const Lin& l) const { return h->d_wb + l.w; }
+  const bf16* W_(const Lin& l) const { return h->d_wb + l.w; }
   const float* Bf(const Lin& l) const { return l.has_bias ? h->d_wf + l.b : nullptr; }
   const float* F(size_t off) const { return h->d_wf + off; }
 
-  void push(const Op& op) { if (!dry() && status == SV_OK) plan->ops.push_back(op); }
+  void push(const Op& op) {
+    if (dry() || status != SV_OK) return;
+    plan->ops.push_back(op);
+    plan->bytes_by_kind[op.kind] += op.alg_bytes;
+  }
 
   void gemm(const bf16* A, int64_t lda, const Lin& l, int M, int act, const float* resid, int64_t ldr, void* out, int64_t ldc, int out_fp32) {
     if (dry() || status != SV_OK) return;
@@ -426,21 +434,26 @@ struct Builder {
     op.kind = OP_GEMM;
     status = gemm_plan(d, &op.gemm);
     plan->gemm_flops += op.gemm.flops;
+    op.alg_bytes = 2.0 * M * d.K + 2.0 * l.N * d.K + static_cast<double>(M) * l.N * (out_fp32 ? 4 : 2) + (resid ? 4.0 * M * l.N : 0.0);
     push(op);
   }
   void ln(const float* x, const Norm& n, float eps, int64_t rows, float* of, bf16* ob, bf16* patch = nullptr, int pH = 0, int pW = 0, int psr = 0) {
     Op op; op.kind = OP_LN; op.src = x; op.p0 = F(n.g); op.p1 = F(n.b); op.f0 = eps; op.l0 = rows; op.i[0] = n.C; op.dst = of; op.dst2 = ob;
     op.dst3 = patch; op.i[1] = pH; op.i[2] = pW; op.i[3] = psr;
+    op.alg_bytes = static_cast<double>(rows) * n.C * (4 + (of ? 4 : 0) + (ob ? 2 : 0) + (patch ? 2 : 0));
     push(op);
   }
   void im2col(const float* nchw, const bf16* nhwc, int B, int Cin, int H, int W, int k, int stride, int pad, bf16* out, int64_t ldo, int ext = EXT_NONE) {
     Op op; op.kind = OP_IM2COL; op.src = nchw; op.src2 = nhwc; op.dst = out; op.l0 = ldo; op.ext_src = ext;
     op.i[0] = B; op.i[1] = Cin; op.i[2] = H; op.i[3] = W; op.i[4] = k; op.i[5] = stride; op.i[6] = pad;
+    op.alg_bytes = static_cast<double>(B) * Cin * H * W * (nhwc ? 2 : 4) +
+                   2.0 * B * conv_out_dim(H, k, stride, pad) * conv_out_dim(W, k, stride, pad) * static_cast<double>(ldo);
     push(op);
   }
   void dwconv(const bf16* x, size_t w, size_t b, int B, int H, int W, int C, bf16* out, int64_t ldo) {
     Op op; op.kind = OP_DWCONV; op.src = x; op.p0 = F(w); op.p1 = F(b); op.dst = out; op.i[0] = B; op.i[1] = H; op.i[2] = W; op.i[3] = C;
     op.l0 = ldo;
+    op.alg_bytes = 2.0 * 2.0 * B * H * W * static_cast<double>(C);
     if (!dry() && status == SV_OK && dwconv_tma_supported(C)) {
       op.dw_tma = true;
       status = dwconv_tma_plan(x, F(w), F(b), B, H, W, C, out, ldo, &op.dw);
@@ -450,10 +463,12 @@ struct Builder {
   void attn(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads, int Nq, int Nkv, int hd) {
     Op op; op.kind = OP_ATTN; op.src = q; op.src2 = k; op.src3 = v; op.dst = o; op.l0 = ldq; op.l1 = ldk; op.l2 = ldv; op.l3 = ldo;
     op.i[0] = B; op.i[1] = heads; op.i[2] = Nq; op.i[3] = Nkv; op.i[4] = hd; op.f0 = 1.0f / sqrtf(static_cast<float>(hd));
+    op.alg_bytes = 2.0 * B * heads * hd * (2.0 * Nq + 2.0 * Nkv);
     push(op);
   }
   void gauss(float* out, int planes, int H, int W) {
     Op op; op.kind = OP_GAUSS; op.dst = out; op.i[0] = planes; op.i[1] = H; op.i[2] = W; op.ext_src = EXT_SEG;
+    op.alg_bytes = 8.0 * planes * H * W;
     push(op);
   }
   void bilinear(const bf16* x, int B, int H, int W, int C, int Ho, int Wo, bf16* out, int64_t ldo) {
@@ -462,6 +477,15 @@ struct Builder {
   }
   void mean(const float* x, int B, int tokens, int C) {
     Op op; op.kind = OP_MEAN; op.src = x; op.i[0] = B; op.i[1] = tokens; op.i[2] = C; op.ext_dst = EXT_OUT;
+    push(op);
+  }
+  // fused k7s4p3 conv on an fp32 NCHW input + LayerNorm (norm != nullptr) or ReLU
+  void stem(const float* src, int ext, const Lin& l, const Norm* norm, int B, int Cin, int H, int W, float* of, bf16* ob) {
+    Op op; op.kind = OP_STEM; op.src = src; op.ext_src = ext; op.src2 = W_(l); op.p0 = Bf(l); op.dst = of; op.dst2 = ob;
+    op.p1 = norm ? F(norm->g) : nullptr; op.src3 = norm ? F(norm->b) : nullptr;
+    op.i[0] = B; op.i[1] = Cin; op.i[2] = H; op.i[3] = W; op.i[4] = l.N; op.i[5] = l.ldw; op.i[6] = norm ? 0 : 1; op.f0 = 1e-5f;
+    const double outpx = static_cast<double>(B) * conv_out_dim(H, 7, 4, 3) * conv_out_dim(W, 7, 4, 3);
+    op.alg_bytes = 4.0 * B * Cin * H * W + outpx * l.N * ((of ? 4 : 0) + (ob ? 2 : 0));
     push(op);
   }
   void tap(const std::string& name, const bf16* p, int64_t elems) { if (!dry()) plan->taps[name] = Tap{p, elems}; }
@@ -536,10 +560,14 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
       const int cinp = s == 0 ? 3 : c.embed_dims[s - 1] / 4;
       const StageW& S = h->st[s];
       const int M = n * g[s].N;
-      if (s == 0) b.im2col(seg_g, nullptr, n, cinp, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.hc.ldw);
-      else b.im2col(nullptr, hc_b16[s - 1], n, cinp, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.hc.ldw);
-      b.gemm(col, S.hc.ldw, S.hc, M, ACT_NONE, nullptr, 0, conv_out, g[s].Cp, 1);
-      b.ln(conv_out, S.hc_norm, 1e-5f, M, hc_f32[s], hc_b16[s]);
+      if (s == 0 && stem_conv_supported(cinp, S.hc.N, S.hc.ldw)) {
+        b.stem(seg_g, EXT_NONE, S.hc, &S.hc_norm, n, cinp, hh, ww, hc_f32[s], hc_b16[s]);
+      } else {
+        if (s == 0) b.im2col(seg_g, nullptr, n, cinp, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.hc.ldw);
+        else b.im2col(nullptr, hc_b16[s - 1], n, cinp, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.hc.ldw);
+        b.gemm(col, S.hc.ldw, S.hc, M, ACT_NONE, nullptr, 0, conv_out, g[s].Cp, 1);
+        b.ln(conv_out, S.hc_norm, 1e-5f, M, hc_f32[s], hc_b16[s]);
+      }
       hh = g[s].H; ww = g[s].W;
     }
   }
@@ -551,10 +579,14 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
       const StageW& S = h->st[s];
       const int M = n * G.N, Mk = n * G.Nkv, C = G.C;
       const int cin = s == 0 ? 3 : c.embed_dims[s - 1];
-      if (s == 0) b.im2col(nullptr, nullptr, n, cin, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.pe.ldw, EXT_X);
-      else b.im2col(nullptr, c_b16[s - 1], n, cin, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.pe.ldw);
-      b.gemm(col, S.pe.ldw, S.pe, M, ACT_NONE, nullptr, 0, conv_out, C, 1);
-      b.ln(conv_out, S.pe_norm, 1e-5f, M, x, xn);
+      if (s == 0 && stem_conv_supported(cin, S.pe.N, S.pe.ldw)) {
+        b.stem(nullptr, EXT_X, S.pe, &S.pe_norm, n, cin, hh, ww, x, xn);
+      } else {
+        if (s == 0) b.im2col(nullptr, nullptr, n, cin, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.pe.ldw, EXT_X);
+        else b.im2col(nullptr, c_b16[s - 1], n, cin, hh, ww, ks[s], strd[s], ks[s] / 2, col, S.pe.ldw);
+        b.gemm(col, S.pe.ldw, S.pe, M, ACT_NONE, nullptr, 0, conv_out, C, 1);
+        b.ln(conv_out, S.pe_norm, 1e-5f, M, x, xn);
+      }
       // init_prompt (:749-756): P = handcrafted_s + embedding_generator_s(x)   (constant over depth)
       b.gemm(xn, C, S.emb, M, ACT_NONE, hc_f32[s], G.Cp, Pb, G.Cp, 0);
       const int ldh = G.hidden + G.Cp;
@@ -606,9 +638,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
     for (int i = 0; i < 4; ++i) {
       const Lin& L = h->flow[i];
       const int M = n * g[i].N;
-      if (i == 0) b.im2col(nullptr, nullptr, n, 2, hh, ww, 7, 4, 3, col, L.ldw, EXT_FLOW);
-      else b.im2col(nullptr, fl[i - 1], n, fch[i], hh, ww, 3, 2, 1, col, L.ldw);
-      b.gemm(col, L.ldw, L, M, ACT_RELU, nullptr, 0, fl[i], fch[i + 1], 0);
+      if (i == 0 && stem_conv_supported(2, L.N, L.ldw)) {
+        b.stem(nullptr, EXT_FLOW, L, nullptr, n, 2, hh, ww, nullptr, fl[i]);
+      } else {
+        if (i == 0) b.im2col(nullptr, nullptr, n, 2, hh, ww, 7, 4, 3, col, L.ldw, EXT_FLOW);
+        else b.im2col(nullptr, fl[i - 1], n, fch[i], hh, ww, 3, 2, 1, col, L.ldw);
+        b.gemm(col, L.ldw, L, M, ACT_RELU, nullptr, 0, fl[i], fch[i + 1], 0);
+      }
       hh = g[i].H; ww = g[i].W;
     }
     for (int j = 0; j < 2; ++j) {
@@ -702,7 +738,16 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
         rc = launch_bilinear_tokens(static_cast<const bf16*>(op.src), op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.i[5],
                                     static_cast<bf16*>(op.dst), op.l0, st);
         break;
+      case OP_STEM: {
+        const float* src = static_cast<const float*>(op.src);
+        if (op.ext_src == EXT_X) src = x;
+        if (op.ext_src == EXT_FLOW) src = flow;
+        rc = launch_stem_conv(src, static_cast<const bf16*>(op.src2), op.i[5], op.p0, op.p1, static_cast<const float*>(op.src3), op.f0, op.i[6],
+                              op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], static_cast<float*>(op.dst), static_cast<bf16*>(op.dst2), st);
+        break;
+      }
       case OP_MEAN: rc = launch_token_mean(static_cast<const float*>(op.src), op.i[0], op.i[1], op.i[2], out, st); break;
+      default: break;
     }
     if (rc != SV_OK) return rc;
     if (prof) SV_CUDA_OK(cudaEventRecord(h->prof_events[2 * op_idx + 1], st));
@@ -720,6 +765,7 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
       p.ops[i].prof_n += 1;
     }
     h->prof_gemm_flops += p.gemm_flops;
+    for (int i = 0; i < OP_KINDS; ++i) h->prof_bytes[i] += p.bytes_by_kind[i];
   }
   return SV_OK;
 }
@@ -880,7 +926,7 @@ int sv_evp_set_profile(sv_evp_handle* h, int32_t enable) {
   using namespace sv;
   SV_CHECK(h, "null handle");
   h->profile = enable != 0;
-  for (int i = 0; i < 8; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+  for (int i = 0; i < OP_KINDS; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; h->prof_bytes[i] = 0.0; }
   h->prof_gemm_flops = 0.0;
   for (auto& kv : h->plans)
     for (const Op& op : kv.second->ops) { op.prof_ms = 0.0; op.prof_n = 0; }
@@ -892,7 +938,7 @@ int sv_evp_dump_profile(const sv_evp_handle* h, const char* path) {
   SV_CHECK(h && path, "null argument");
   FILE* f = fopen(path, "w");
   if (!f) return fail(SV_ERR_INVALID, std::string("cannot open ") + path);
-  static const char* kinds[] = {"gemm", "layernorm", "im2col", "dwconv", "attention", "gauss", "bilinear", "mean"};
+  static const char* kinds[] = {"gemm", "layernorm", "im2col", "dwconv", "attention", "gauss", "bilinear", "mean", "stem"};
   fprintf(f, "plan_n,op,kind,M,N,K,block_n,stages,grid,act,out_fp32,resid,i0,i1,i2,i3,i4,calls,ms_total\n");
   for (const auto& kv : h->plans) {
     const Plan& p = *kv.second;
@@ -912,10 +958,14 @@ int sv_evp_dump_profile(const sv_evp_handle* h, const char* path) {
   return SV_OK;
 }
 
-int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops) {
+int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops, double* bytes_by_kind) {
   using namespace sv;
   SV_CHECK(h && ms_by_kind && launches_by_kind && gemm_flops, "null argument");
-  for (int i = 0; i < 8; ++i) { ms_by_kind[i] = h->prof_ms[i]; launches_by_kind[i] = h->prof_n[i]; }
+  for (int i = 0; i < OP_KINDS; ++i) {
+    ms_by_kind[i] = h->prof_ms[i];
+    launches_by_kind[i] = h->prof_n[i];
+    if (bytes_by_kind) bytes_by_kind[i] = h->prof_bytes[i];
+  }
   *gemm_flops = h->prof_gemm_flops;
   return SV_OK;
 }

@@ -34,6 +34,11 @@ bool dwconv_tma_supported(int C);
 int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo, DwconvPlan* plan);
 int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st);
 
+// fused first-layer conv (k7 s4 p3 on fp32 NCHW, <= 3 channels) + LayerNorm (mode 0) or ReLU (mode 1)  (stem.cu)
+bool stem_conv_supported(int Cin, int Cout, int ldw);
+int launch_stem_conv(const float* src, const bf16* w, int ldw, const float* bias, const float* gamma, const float* beta, float eps, int mode,
+                     int B, int Cin, int H, int W, int Cout, float* out_f32, bf16* out_bf16, cudaStream_t st);
+
 inline int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 
 }  // namespace sv

@@ -81,8 +81,15 @@ class LFBExtractor:
             out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
         compute = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
-        for bi, b0 in enumerate(range(0, N, self.batch_size)):
-            n = min(self.batch_size, N - b0)
+        # ramp-up schedule: small first batches so the kernels start while the bulk of the input is still crossing PCIe
+        # (only the first copy of a call is not overlapped with compute)
+        starts, b0, ramp = [], 0, max(1, self.batch_size // 4)
+        while b0 < N:
+            n = min(ramp, self.batch_size, N - b0)
+            starts.append((b0, n))
+            b0 += n
+            ramp *= 2
+        for bi, (b0, n) in enumerate(starts):
             x, s, f, ev_in, ev_free = bufs[bi % 2]
             with torch.cuda.stream(self._copy_stream):
                 if bi >= 2:

@@ -269,14 +269,18 @@ class MixVisionTransformerEVP(nn.Module):
         lib = _native.lib()
         B, _, H, W = x.shape
         mb = max(1, min(int(micro_batch), B))
-        key = (mb, H, W)
+        # one grow-only workspace per device and resolution: smaller batches reuse it, so the cached launch plans (keyed by
+        # frame count and workspace address inside the handle) stay valid across calls with different B
+        key = (H, W)
+        nbytes = lib.sv_evp_workspace_bytes(st["handle"], mb, H, W)
+        if nbytes == 0:
+            raise RuntimeError("sv_evp_workspace_bytes failed: " + _native.last_error())
         ws = st["workspace"].get(key)
-        if ws is None:
-            nbytes = lib.sv_evp_workspace_bytes(st["handle"], mb, H, W)
-            if nbytes == 0:
-                raise RuntimeError("sv_evp_workspace_bytes failed: " + _native.last_error())
+        if ws is None or ws.numel() < nbytes:
+            ws = None
+            st["workspace"].pop(key, None)
             ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-            st["workspace"] = {key: ws}  # keep one workspace alive per device
+            st["workspace"][key] = ws
         out = torch.empty((B, self.embedding_dim), dtype=torch.float32, device=x.device)
         rc = lib.sv_evp_forward(st["handle"], ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(seg.data_ptr()),
                                 ctypes.c_void_p(0 if flow is None else flow.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, H, W, mb,

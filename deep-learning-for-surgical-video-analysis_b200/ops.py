@@ -160,3 +160,23 @@ def token_mean(x: torch.Tensor, tokens: int) -> torch.Tensor:
     rc = _native.lib().sv_op_token_mean(_ptr(x), B, tokens, C, _ptr(out), _stream_ptr(x.device))
     _native.check(rc, "sv_op_token_mean")
     return out
+
+
+def stem_conv(src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
+              eps: float = 1e-5, relu: bool = False):
+    """src [B,Cin,H,W] fp32; weight [Cout,Cin,7,7] fp32 (packed here to the kernel's (kh,kw,cin) bf16 layout) -> (fp32, bf16) token-major
+    [B*Ho*Wo, Cout] of LayerNorm(conv(src)+bias) (or ReLU(conv+bias) when relu)."""
+    _require_cuda(src, weight, bias, gamma, beta)
+    B, Cin, H, W = src.shape
+    Cout = weight.shape[0]
+    K = 49 * Cin
+    ldw = (K + 7) // 8 * 8
+    wp = torch.zeros((Cout, ldw), dtype=torch.bfloat16, device=src.device)
+    wp[:, :K] = weight.permute(0, 2, 3, 1).reshape(Cout, K).to(torch.bfloat16)
+    Ho, Wo = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+    of = torch.empty((B * Ho * Wo, Cout), dtype=torch.float32, device=src.device)
+    ob = torch.empty((B * Ho * Wo, Cout), dtype=torch.bfloat16, device=src.device)
+    rc = _native.lib().sv_op_stem_conv(_ptr(src), _ptr(wp), ldw, _ptr(bias), _ptr(gamma), _ptr(beta), eps, int(relu), B, Cin, H, W, Cout, _ptr(of),
+                                       _ptr(ob), _stream_ptr(src.device))
+    _native.check(rc, "sv_op_stem_conv")
+    return of, ob

@@ -37,6 +37,7 @@ extern "C" {
 #define SV_ERR_UNSUPPORTED 4 /* configuration outside what the kernels implement */
 
 #define SV_ABI_VERSION 1
+#define SV_PROFILE_CLASSES 9
 
 const char* sv_last_error(void);
 int sv_abi_version(void);
@@ -97,11 +98,14 @@ int64_t sv_evp_last_launch_count(const sv_evp_handle* h);
 
 /* Per-kernel-class device timing for roofline reports: when enabled, every launch of sv_evp_forward is bracketed by
  * CUDA events on `stream` and the forward synchronises at the end of each micro-batch (never enable in a timed run).
- * Classes (index): 0 tcgen05 GEMM, 1 LayerNorm, 2 im2col, 3 DWConv+GELU, 4 attention, 5 Gaussian, 6 bilinear, 7 token mean.
- * sv_evp_set_profile resets the accumulators; sv_evp_get_profile fills ms_by_kind[8], launches_by_kind[8] and the
- * algorithmic GEMM FLOPs (2*M*N*K summed over the GEMM launches) since the last reset. */
+ * Classes (index): 0 tcgen05 GEMM, 1 LayerNorm, 2 im2col, 3 DWConv+GELU, 4 attention, 5 Gaussian, 6 bilinear, 7 token mean,
+ * 8 fused first-layer conv (stem).  Arrays passed to sv_evp_get_profile must hold SV_PROFILE_CLASSES entries.
+ * sv_evp_set_profile resets the accumulators; sv_evp_get_profile fills ms_by_kind[], launches_by_kind[], the algorithmic
+ * GEMM FLOPs (2*M*N*K summed over the GEMM launches) and, if bytes_by_kind != NULL, the algorithmic HBM bytes per class
+ * (operands + results of every launch counted once) since the last reset. */
 int sv_evp_set_profile(sv_evp_handle* h, int32_t enable);
-int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops);
+int sv_evp_get_profile(const sv_evp_handle* h, double* ms_by_kind, int64_t* launches_by_kind, double* gemm_flops,
+                       double* bytes_by_kind);
 /* CSV with one line per launch of the schedule (shape, tile configuration, accumulated device ms) since the last reset. */
 int sv_evp_dump_profile(const sv_evp_handle* h, const char* path);
 
@@ -175,6 +179,14 @@ int sv_op_gauss5x5(const float* x, float* out, int32_t planes, int32_t H, int32_
  * stride ldo (segformer_head.py:149-156 semantics, applied before the per-pixel projection). */
 int sv_op_bilinear_tokens(const uint16_t* x, int32_t B, int32_t H, int32_t W, int32_t C, int32_t Ho, int32_t Wo,
                           uint16_t* out, int64_t ldo, void* stream);
+
+/* Fused first-layer conv: Conv2d(Cin<=3 -> Cout in {16,32,64}, k7, s4, p3) on fp32 NCHW + bias, then LayerNorm(eps) over Cout
+ * (relu == 0; gamma/beta required) or ReLU (relu != 0).  w: [Cout, ldw] bf16 with k = (kh, kw, cin), zero padded, ldw % 8 == 0.
+ * Outputs are token-major [B*Ho*Wo, Cout]; either may be NULL.  replaces OverlapPatchEmbed(patch_size=7, stride=4)
+ * (mix_transformer_evp.py:209-215) and flow_encoder.conv1+bn1+act (:846). */
+int sv_op_stem_conv(const float* src, const uint16_t* w, int32_t ldw, const float* bias, const float* gamma, const float* beta,
+                    float eps, int32_t relu, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, float* out_f32,
+                    uint16_t* out_bf16, void* stream);
 
 /* mean over `tokens` consecutive rows of fp32 [B*tokens, C] -> [B, C] (AdaptiveAvgPool2d(1), segformer_head.py:167). */
 int sv_op_token_mean(const float* x, int32_t B, int32_t tokens, int32_t C, float* out, void* stream);

@@ -180,3 +180,20 @@ def test_token_mean():
     out = ops.token_mean(x, 49)
     torch.cuda.synchronize()
     assert (out - x.view(5, 49, 2048).mean(1)).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(3, 64, 224, 224, False), (3, 16, 224, 224, False), (2, 64, 224, 224, True), (3, 64, 100, 76, False), (2, 32, 61, 37, True)])
+def test_stem_conv(cfg):
+    Cin, Cout, H, W, relu = cfg
+    B = 3
+    x = _rand((B, Cin, H, W), 90)
+    w = _rand((Cout, Cin, 7, 7), 91, 1.0 / math.sqrt(49 * Cin))
+    bias = _rand((Cout,), 92, 0.3)
+    g, b = _rand((Cout,), 93) * 0.2 + 1.0, _rand((Cout,), 94, 0.3)
+    of, ob = ops.stem_conv(x, w, bias, None if relu else g, None if relu else b, 1e-5, relu)
+    torch.cuda.synchronize()
+    y = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), bias, stride=4, padding=3)   # bf16 operands, fp32 accumulate
+    y = y.flatten(2).transpose(1, 2)
+    ref = (F.relu(y) if relu else F.layer_norm(y, (Cout,), g, b, 1e-5)).reshape(-1, Cout)
+    assert (of - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    assert (ob.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
