@@ -18,6 +18,7 @@ struct GemmDesc {
   void* out = nullptr;              // bf16 or fp32, row stride ldc
   int64_t ldc = 0;
   int out_fp32 = 0;
+  int pair = -1;  // CTA-pair mode (tcgen05 cta_group::2, 256-row tiles, B split across the pair): -1 auto, 0 off, 1 on
 };
 
 struct GemmParams {
@@ -26,6 +27,8 @@ struct GemmParams {
   int num_stages;   // smem ring depth
   int num_n_tiles;
   int num_tiles;
+  int pair;         // 1: 2-CTA clusters; num_tiles counts 256-row pair tiles
+  int prefetch;     // k-blocks of the A operand requested into L2 ahead of the shared-memory ring (0 = off)
   int act;
   int out_fp32;
   const float* bias;

@@ -15,6 +15,7 @@
 // (a warp may only touch TMEM lanes 32*(warp%4) .. +31; two warps share each lane quarter and split the 32-column chunks,
 // so every SM sub-partition has two epilogue warps to hide each other's latencies).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <mutex>
@@ -94,7 +95,11 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, const float* stg,
   }
 }
 
-template <int ACT, bool OUT_F32, bool RESID>
+// PAIR = true: the kernel runs as 2-CTA clusters (tcgen05 cta_group::2).  Each CTA stages its own 128 rows of A and HALF of
+// the B tile (block_n/2 rows); the leader CTA (cluster rank 0) issues one M=256 MMA per k-step that reads both CTAs' shared
+// memory and writes 128 accumulator rows into each CTA's TMEM.  Shared-memory fill traffic per MAC drops by 1/4..1/3, which is
+// what bounds the K >= 256 GEMMs of stages 3/4 (operands come from L2, not HBM).
+template <int ACT, bool OUT_F32, bool RESID, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -107,7 +112,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int S = p.num_stages;
-  const int b_tile_bytes = p.block_n * kBlockK * 2;
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const int b_rows = PAIR ? p.block_n / 2 : p.block_n;   // B-tile rows staged by THIS CTA
+  const int b_tile_bytes = b_rows * kBlockK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;
   // 128B swizzle needs 1024-byte aligned tiles
   // (offset arithmetic on the __shared__ array keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
@@ -127,49 +134,74 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full_bar[a], 1);
-        ptx::mbar_init(&tmem_empty_bar[a], kEpiWarps);  // one arrive per epilogue warp
+        ptx::mbar_init(&tmem_empty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
       }
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(&tmem_base_slot, kTmemCols);
-    ptx::tmem_relinquish();
+    if (PAIR) {
+      ptx::tmem_alloc_pair(&tmem_base_slot, kTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(&tmem_base_slot, kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();   // peer barriers must exist before any remote arrive / multicast commit
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
   const int num_kb = (p.K + kBlockK - 1) / kBlockK;
+  // persistent schedule: CTAs (or CTA pairs) stride over the tiles (256-row pair tiles when PAIR)
+  const int first_tile = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * kBlockM;
-        const int n0 = (tile % p.num_n_tiles) * p.block_n;
+      // L2 prefetch cursor: runs p.prefetch k-blocks ahead of the load cursor over this CTA's (tile, k-block) sequence
+      int pf_tile = first_tile, pf_kb = 0;
+      auto prefetch_next = [&]() {
+        if (pf_tile >= p.num_tiles) return;
+        const int pm0 = (pf_tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
+        ptx::tma_prefetch_l2_2d(&tmap_a, pf_kb * kBlockK, pm0);
+        if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_step; }
+      };
+      for (int i = 0; i < p.prefetch; ++i) prefetch_next();
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+        const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
+        const int n0 = (tile % p.num_n_tiles) * p.block_n + static_cast<int>(cta_rank) * b_rows;
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (p.prefetch > 0) prefetch_next();
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-          ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
-          ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+          if (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
+            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+            ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+            ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+            ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16_f32(kBlockM, p.block_n);
+    if (lane == 0 && cta_rank == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(PAIR ? 2 * kBlockM : kBlockM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
@@ -183,10 +215,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int ksteps = k_left >= kBlockK ? kBlockK / 16 : (k_left + 15) / 16;
           for (int kk = 0; kk < ksteps; ++kk) {
             // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) start-address field
-            ptx::umma_f16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            if (PAIR) ptx::umma_f16_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            else ptx::umma_f16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
-          if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+          if (PAIR) {
+            ptx::umma_commit_pair(&empty_bar[stage], 0x3);                          // both CTAs' smem slots
+            if (kb == num_kb - 1) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+          } else {
+            ptx::umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+          }
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         acc ^= 1;
@@ -203,8 +241,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int c4 = (lane & 7) * 4;  // 8 lanes x 4 columns = one 32-column row segment
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * kBlockM;
+    const uint32_t leader_tmem_empty0 = PAIR ? ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[0]), 0u) : 0u;
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+      const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
       const int n0 = (tile % p.num_n_tiles) * p.block_n;
       const int n_valid = min(p.block_n, p.N - n0);
       const int nchunks = (n_valid + 31) >> 5;
@@ -216,6 +255,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr && c < n_valid) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
         *reinterpret_cast<float4*>(bias_s + c) = b;
+      }
+      if constexpr (RESID) {
+        // pull this warp's share of the residual tile into L2 now, while the MMAs of the tile are still running: the residual
+        // stream comes from HBM and one chunk of register prefetch cannot cover that latency
+        const int prow = m0 + quarter * 32 + lane;
+        if (prow < p.M) {
+          const float* rp = p.residual + static_cast<long long>(prow) * p.ldr + n0;
+          for (int j = half; j * 32 < n_valid; j += 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 32));
+        }
       }
       float4 res_a[8], res_b[8];
       epi_load_residual<RESID>(res_a, p, row_base, n0 + half * 32 + c4, half * 32 + c4 < n_valid);
@@ -252,17 +300,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // every TMEM read of this warp has completed (the last tcgen05.wait::ld is behind us): release the accumulator
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(leader_tmem_empty0 + static_cast<uint32_t>(acc) * 8u);  // the leader's MMA warp owns both TMEMs
+        else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (PAIR) ptx::cluster_sync(); else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -349,16 +401,28 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms);
   const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
-  p.num_stages = std::min(kMaxStages, kSmemBudget / stage_bytes);
+  // CTA-pair mode pays off when operand staging (L2 -> smem) dominates: deep K and enough 256-row tiles to fill the machine
+  // Measured on B200 (profiles/r01/gemm_pair_vs_single.log): at this path's shapes the pair mode is 5-20 % SLOWER than single-CTA
+  // tiles, so 'auto' resolves to off; the mode stays available (and tested) behind GemmDesc::pair / SURGVID_GEMM_PAIR.
+  p.pair = d.pair > 0 ? 1 : 0;
+  if (p.pair && (p.block_n % 32 != 0)) p.block_n = round_up(p.block_n, 32);  // each CTA stages block_n/2 rows of B (multiple of 16)
+  if (p.block_n > 256) { p.block_n = 256; }
+  const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
+  const int stage_bytes_eff = kATileBytes + b_rows * kBlockK * 2;
+  p.num_stages = std::min(kMaxStages, kSmemBudget / stage_bytes_eff);
   p.num_n_tiles = ceil_div(d.N, p.block_n);
-  p.num_tiles = ceil_div(d.M, kBlockM) * p.num_n_tiles;
+  p.num_tiles = ceil_div(d.M, p.pair ? 2 * kBlockM : kBlockM) * p.num_n_tiles;
+  {
+    static const int pf_env = getenv("SURGVID_GEMM_PREFETCH") ? atoi(getenv("SURGVID_GEMM_PREFETCH")) : 0;  // measured: no gain (0 = off)
+    p.prefetch = pf_env;
+  }
   p.act = d.act; p.out_fp32 = d.out_fp32;
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.out = d.out; p.ldc = d.ldc;
-  plan->grid = std::min(p.num_tiles, sms);
-  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes + kEpiSmemBytes + 1024;
+  plan->grid = p.pair ? 2 * std::min(p.num_tiles, sms / 2) : std::min(p.num_tiles, sms);
+  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes_eff + kEpiSmemBytes + 1024;
   plan->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K, d.lda, kBlockM));
-  SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, p.block_n));
+  SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, b_rows));
   return SV_OK;
 }
 
@@ -366,18 +430,25 @@ namespace {
 
 typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
 
-template <int ACT>
+template <int ACT, bool PAIR>
 GemmKernelFn pick_kernel(int out_fp32, bool resid) {
-  if (out_fp32) return resid ? gemm_bf16_tcgen05_kernel<ACT, true, true> : gemm_bf16_tcgen05_kernel<ACT, true, false>;
-  return resid ? gemm_bf16_tcgen05_kernel<ACT, false, true> : gemm_bf16_tcgen05_kernel<ACT, false, false>;
+  if (out_fp32) return resid ? gemm_bf16_tcgen05_kernel<ACT, true, true, PAIR> : gemm_bf16_tcgen05_kernel<ACT, true, false, PAIR>;
+  return resid ? gemm_bf16_tcgen05_kernel<ACT, false, true, PAIR> : gemm_bf16_tcgen05_kernel<ACT, false, false, PAIR>;
 }
 
 GemmKernelFn kernel_for(const GemmParams& p) {
   const bool resid = p.residual != nullptr;
+  if (p.pair) {
+    switch (p.act) {
+      case ACT_GELU: return pick_kernel<ACT_GELU, true>(p.out_fp32, resid);
+      case ACT_RELU: return pick_kernel<ACT_RELU, true>(p.out_fp32, resid);
+      default: return pick_kernel<ACT_NONE, true>(p.out_fp32, resid);
+    }
+  }
   switch (p.act) {
-    case ACT_GELU: return pick_kernel<ACT_GELU>(p.out_fp32, resid);
-    case ACT_RELU: return pick_kernel<ACT_RELU>(p.out_fp32, resid);
-    default: return pick_kernel<ACT_NONE>(p.out_fp32, resid);
+    case ACT_GELU: return pick_kernel<ACT_GELU, false>(p.out_fp32, resid);
+    case ACT_RELU: return pick_kernel<ACT_RELU, false>(p.out_fp32, resid);
+    default: return pick_kernel<ACT_NONE, false>(p.out_fp32, resid);
   }
 }
 
@@ -395,6 +466,23 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
       configured.push_back(reinterpret_cast<const void*>(fn));
     }
   }
+  if (plan.p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = plan.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_w, plan.p);
+    if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaLaunchKernelEx(gemm pair): ") + cudaGetErrorString(e));
+    return SV_OK;
+  }
   fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_w, plan.p);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
@@ -409,6 +497,7 @@ extern "C" int sv_op_gemm_bf16(const uint16_t* A, int64_t lda, const uint16_t* W
   d.W = reinterpret_cast<const sv::bf16*>(W); d.ldw = ldw;
   d.M = M; d.N = N; d.K = K; d.bias = bias; d.act = act; d.residual = residual; d.ldr = ldr;
   d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
+  if (const char* e = getenv("SURGVID_GEMM_PAIR")) d.pair = atoi(e);  // test hook: force CTA-pair mode on (1) / off (0)
   sv::GemmPlan plan;
   SV_TRY(sv::gemm_plan(d, &plan));
   return sv::gemm_launch(plan, static_cast<cudaStream_t>(stream));

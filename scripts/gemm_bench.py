@@ -10,6 +10,8 @@ dev = "cuda:0"
 shapes = [  # M, N, K, out_fp32, resid
     (627200, 256, 64, 0, 0), (627200, 64, 64, 0, 0), (627200, 64, 256, 1, 1), (39200, 1280, 320, 0, 0), (39200, 320, 1280, 1, 1),
     (39200, 320, 320, 0, 0), (39200, 320, 320, 1, 1), (156800, 512, 128, 0, 0), (9800, 2048, 8192, 1, 0), (75776, 1280, 320, 0, 0),
+    (156800, 1280, 320, 0, 0), (156800, 320, 1360, 1, 1), (156800, 320, 320, 1, 1), (156800, 320, 320, 0, 0), (450800, 320, 1360, 1, 1),
+    (450800, 1280, 320, 0, 0), (39200, 2048, 8192, 1, 0), (112700, 512, 2176, 1, 1), (112700, 2048, 512, 0, 0),
 ]
 if len(sys.argv) > 1:
     shapes = [shapes[int(i)] for i in sys.argv[1].split(",")]

@@ -197,3 +197,23 @@ def test_stem_conv(cfg):
     ref = (F.relu(y) if relu else F.layer_norm(y, (Cout,), g, b, 1e-5)).reshape(-1, Cout)
     assert (of - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
     assert (ob.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 64, 64), (129, 24, 72), (1000, 320, 1280), (39200, 320, 1360), (5000, 1280, 320), (777, 512, 2048), (148 * 256 * 2 + 300, 256, 192)])
+def test_gemm_cta_pair_mode(M, N, K, monkeypatch):
+    """tcgen05 cta_group::2 path (2-CTA clusters, 256-row tiles) forced on; must agree with the single-CTA path bit for bit."""
+    a = _rand((M, K), 101, dtype=torch.bfloat16)
+    w = _rand((N, K), 102, 1.0 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = _rand((N,), 103, 0.5)
+    resid = _rand((M, N), 104)
+    monkeypatch.setenv("SURGVID_GEMM_PAIR", "0")
+    single = ops.gemm_bf16(a, w, bias=bias, residual=resid, out_dtype=torch.float32)
+    monkeypatch.setenv("SURGVID_GEMM_PAIR", "1")
+    pair = ops.gemm_bf16(a, w, bias=bias, residual=resid, out_dtype=torch.float32)
+    pair_bf16 = ops.gemm_bf16(a, w, bias=bias, act=1)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + resid
+    assert (pair - ref).abs().max().item() < 3e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(pair, single)
+    ref2 = F.gelu(a.float() @ w.float().t() + bias)
+    assert (pair_bf16.float() - ref2).abs().max().item() < 3e-2 * max(1.0, ref2.abs().max().item())
