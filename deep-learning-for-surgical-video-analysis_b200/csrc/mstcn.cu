@@ -5,6 +5,8 @@
 // video boundaries, so one launch per layer covers every video.  The causal branch (mstcn_causal_conv=True) is
 //   y[t] = x[t] + W1 * relu(Wd[0] x[t-2d] + Wd[1] x[t-d] + Wd[2] x[t] + bd) + b1        (mstcn.py:208-214)
 // which equals conv(pad 2d) -> relu -> drop last 2d samples -> 1x1 -> add.
+#include <string.h>
+
 #include <map>
 #include <string>
 #include <vector>
@@ -70,9 +72,112 @@ __global__ void __launch_bounds__(256) mstcn_inproj_kernel(const float* __restri
   }
 }
 
-// ---- one DilatedResidualLayer for every frame of every video. One thread = one time step, all F channels.
-// smem: Wd [3][F_in][F_out], W1 [F_in][F_out], bd[F], b1[F] (weights broadcast-read, conflict-free).
+// ---- stage-1 input projection on tensor cores with fp32-level accuracy ("3xTF32"): each fp32 operand is split into a TF32
+// high part and a TF32 residual, and  x*w ~= xh*wh + xh*wl + xl*wh  (dropped term ~2^-22 relative), three mma.sync.m16n8k8.tf32
+// per tile step.  The 8 KB/frame feature read is the only HBM traffic, and with the arithmetic off the FP32 pipe the kernel
+// is bound by it (the SIMT version above needs 16 FLOP per byte from a 72 TFLOP/s pipe and is compute-bound at ~0.1 of HBM).
+// feats tiles arrive through a 3-stage cp.async ring; W is pre-split on the host.
+__device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
+
 template <int F>
+__global__ void __launch_bounds__(128) mstcn_inproj_tf32x3_kernel(const float* __restrict__ feats, const float* __restrict__ Whi,
+                                                                  const float* __restrict__ Wlo, const float* __restrict__ bias, int64_t T, int D,
+                                                                  float* __restrict__ out) {
+  constexpr int BM = 128, BK = 32, ST = 3, NT = F / 8, MT = 2;   // each warp: 2 m16 tiles (32 rows) x F columns
+  constexpr int LDA = BK + 4, LDW = F + 8;  // conflict-free fragment loads
+  extern __shared__ __align__(16) float sm[];
+  float* As = sm;                       // [ST][BM][LDA]
+  float* Wh = As + ST * BM * LDA;       // [ST][BK][LDW]
+  float* Wl = Wh + ST * BK * LDW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
+  const int nk = D / BK;
+
+  auto issue = [&](int kt, int stg) {
+    const int k0 = kt * BK;
+    for (int i = tid; i < BM * (BK / 4); i += 128) {      // 128 rows x 8 chunks of 16 B
+      const int r = i >> 3, c4 = i & 7;
+      const bool ok = row0 + r < T;
+      cp_async_16(As + (stg * BM + r) * LDA + c4 * 4, ok ? feats + (row0 + r) * D + k0 + c4 * 4 : feats, ok);
+    }
+    for (int i = tid; i < BK * (F / 4); i += 128) {       // 32 k x F/4 chunks, hi and lo
+      const int kk = i / (F / 4), f4 = i % (F / 4);
+      cp_async_16(Wh + (stg * BK + kk) * LDW + f4 * 4, Whi + static_cast<int64_t>(k0 + kk) * F + f4 * 4, true);
+      cp_async_16(Wl + (stg * BK + kk) * LDW + f4 * 4, Wlo + static_cast<int64_t>(k0 + kk) * F + f4 * 4, true);
+    }
+  };
+  float acc[MT][NT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { acc[m][i][0] = acc[m][i][1] = acc[m][i][2] = acc[m][i][3] = 0.f; }
+
+  for (int s = 0; s < ST - 1; ++s) {
+    if (s < nk) issue(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");
+    __syncthreads();                                       // stage kt%ST landed for everyone; stage (kt-1)%ST is free again
+    if (kt + ST - 1 < nk) issue(kt + ST - 1, (kt + ST - 1) % ST);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* a_s = As + ((kt % ST) * BM + warp * 32) * LDA;
+    const float* wh_s = Wh + (kt % ST) * BK * LDW;
+    const float* wl_s = Wl + (kt % ST) * BK * LDW;
+#pragma unroll
+    for (int kk = 0; kk < BK / 8; ++kk) {
+      uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const float* am = a_s + m * 16 * LDA;
+        const float a[4] = {am[g * LDA + kk * 8 + t], am[(g + 8) * LDA + kk * 8 + t], am[g * LDA + kk * 8 + t + 4], am[(g + 8) * LDA + kk * 8 + t + 4]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ah[m][j] = to_tf32(a[j]);
+          al[m][j] = to_tf32(a[j] - __uint_as_float(ah[m][j]));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t bh0 = __float_as_uint(wh_s[(kk * 8 + t) * LDW + nt * 8 + g]), bh1 = __float_as_uint(wh_s[(kk * 8 + t + 4) * LDW + nt * 8 + g]);
+        const uint32_t bl0 = __float_as_uint(wl_s[(kk * 8 + t) * LDW + nt * 8 + g]), bl1 = __float_as_uint(wl_s[(kk * 8 + t + 4) * LDW + nt * 8 + g]);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          mma_tf32_1688(acc[m][nt], al[m], bh0, bh1);   // small terms first
+          mma_tf32_1688(acc[m][nt], ah[m], bl0, bl1);
+          mma_tf32_1688(acc[m][nt], ah[m], bh0, bh1);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int m = 0; m < MT; ++m) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int col = nt * 8 + t * 2;
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + col));
+      const int64_t r0 = row0 + warp * 32 + m * 16 + g, r1 = r0 + 8;
+      if (r0 < T) *reinterpret_cast<float2*>(out + r0 * F + col) = make_float2(acc[m][nt][0] + b.x, acc[m][nt][1] + b.y);
+      if (r1 < T) *reinterpret_cast<float2*>(out + r1 * F + col) = make_float2(acc[m][nt][2] + b.x, acc[m][nt][3] + b.y);
+    }
+  }
+}
+
+// ---- one DilatedResidualLayer for every frame of every video.  One thread = NS consecutive time steps, all F channels
+// (NS = 2 for F = 32: every broadcast weight read from shared memory then feeds two FMAs per output channel).
+// smem: Wd [3][F_in][F_out], W1 [F_in][F_out], bd[F], b1[F] (weights broadcast-read, conflict-free).
+template <int F, int NS>
 __global__ void __launch_bounds__(128) mstcn_layer_kernel(const float* __restrict__ x, const int* __restrict__ frame_start,
                                                           const float* __restrict__ wpack, int dilation, int64_t T, float* __restrict__ y) {
   extern __shared__ __align__(16) float sw[];
@@ -83,56 +188,88 @@ __global__ void __launch_bounds__(128) mstcn_layer_kernel(const float* __restric
   const float* W1 = sw + 3 * F * F;
   const float* bd = W1 + F * F;
   const float* b1 = bd + F;
-  const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (t >= T) return;
-  const int64_t start = frame_start[t];
-  float acc[F];
+  const int64_t t0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * NS;
+  if (t0 >= T) return;
+  float acc[NS][F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) acc[f] = bd[f];
-  float xt[F];  // x[t], kept for the residual
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[s][f] = bd[f];
 #pragma unroll
   for (int tap = 0; tap < 3; ++tap) {
-    const int64_t ts = t - static_cast<int64_t>(2 - tap) * dilation;
-    if (ts < start) continue;  // zero left padding (and never read across a video boundary)
-    const float4* xp = reinterpret_cast<const float4*>(x + ts * F);
+    const float* xp[NS];
+    bool ok[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int64_t tt = t0 + s;
+      const int64_t ts = tt - static_cast<int64_t>(2 - tap) * dilation;
+      ok[s] = tt < T && ts >= static_cast<int64_t>(frame_start[tt < T ? tt : T - 1]);  // zero left padding, never across a video boundary
+      xp[s] = x + (ok[s] ? ts : 0) * F;
+    }
 #pragma unroll
     for (int c4 = 0; c4 < F / 4; ++c4) {
-      const float4 xv = __ldg(xp + c4);
-      const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-      if (tap == 2) { xt[c4 * 4] = xv.x; xt[c4 * 4 + 1] = xv.y; xt[c4 * 4 + 2] = xv.z; xt[c4 * 4 + 3] = xv.w; }
+      float xs[NS][4];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const float4 xv = ok[s] ? __ldg(reinterpret_cast<const float4*>(xp[s]) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xs[s][0] = xv.x; xs[s][1] = xv.y; xs[s][2] = xv.z; xs[s][3] = xv.w;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4* wr = reinterpret_cast<const float4*>(Wd + (tap * F + c4 * 4 + j) * F);
 #pragma unroll
         for (int f4 = 0; f4 < F / 4; ++f4) {
           const float4 w = wr[f4];
-          acc[f4 * 4 + 0] = fmaf(xs[j], w.x, acc[f4 * 4 + 0]);
-          acc[f4 * 4 + 1] = fmaf(xs[j], w.y, acc[f4 * 4 + 1]);
-          acc[f4 * 4 + 2] = fmaf(xs[j], w.z, acc[f4 * 4 + 2]);
-          acc[f4 * 4 + 3] = fmaf(xs[j], w.w, acc[f4 * 4 + 3]);
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            acc[s][f4 * 4 + 0] = fmaf(xs[s][j], w.x, acc[s][f4 * 4 + 0]);
+            acc[s][f4 * 4 + 1] = fmaf(xs[s][j], w.y, acc[s][f4 * 4 + 1]);
+            acc[s][f4 * 4 + 2] = fmaf(xs[s][j], w.z, acc[s][f4 * 4 + 2]);
+            acc[s][f4 * 4 + 3] = fmaf(xs[s][j], w.w, acc[s][f4 * 4 + 3]);
+          }
         }
       }
     }
   }
-  float out[F];
+  // out = x[t] + b1 + W1 * relu(acc)
+  float out[NS][F];
 #pragma unroll
-  for (int f = 0; f < F; ++f) out[f] = xt[f] + b1[f];
+  for (int s = 0; s < NS; ++s) {
+    const int64_t tt = t0 + s < T ? t0 + s : T - 1;
+    const float4* xr = reinterpret_cast<const float4*>(x + tt * F);
+#pragma unroll
+    for (int f4 = 0; f4 < F / 4; ++f4) {
+      const float4 v = __ldg(xr + f4);
+      out[s][f4 * 4 + 0] = v.x + b1[f4 * 4 + 0]; out[s][f4 * 4 + 1] = v.y + b1[f4 * 4 + 1];
+      out[s][f4 * 4 + 2] = v.z + b1[f4 * 4 + 2]; out[s][f4 * 4 + 3] = v.w + b1[f4 * 4 + 3];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < F; ++c) {
-    const float h = fmaxf(acc[c], 0.f);
+    float h[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) h[s] = fmaxf(acc[s][c], 0.f);
     const float4* wr = reinterpret_cast<const float4*>(W1 + c * F);
 #pragma unroll
     for (int f4 = 0; f4 < F / 4; ++f4) {
       const float4 w = wr[f4];
-      out[f4 * 4 + 0] = fmaf(h, w.x, out[f4 * 4 + 0]);
-      out[f4 * 4 + 1] = fmaf(h, w.y, out[f4 * 4 + 1]);
-      out[f4 * 4 + 2] = fmaf(h, w.z, out[f4 * 4 + 2]);
-      out[f4 * 4 + 3] = fmaf(h, w.w, out[f4 * 4 + 3]);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        out[s][f4 * 4 + 0] = fmaf(h[s], w.x, out[s][f4 * 4 + 0]);
+        out[s][f4 * 4 + 1] = fmaf(h[s], w.y, out[s][f4 * 4 + 1]);
+        out[s][f4 * 4 + 2] = fmaf(h[s], w.z, out[s][f4 * 4 + 2]);
+        out[s][f4 * 4 + 3] = fmaf(h[s], w.w, out[s][f4 * 4 + 3]);
+      }
     }
   }
-  float4* yp = reinterpret_cast<float4*>(y + t * F);
 #pragma unroll
-  for (int f4 = 0; f4 < F / 4; ++f4) yp[f4] = make_float4(out[f4 * 4], out[f4 * 4 + 1], out[f4 * 4 + 2], out[f4 * 4 + 3]);
+  for (int s = 0; s < NS; ++s) {
+    if (t0 + s < T) {
+      float4* yp = reinterpret_cast<float4*>(y + (t0 + s) * F);
+#pragma unroll
+      for (int f4 = 0; f4 < F / 4; ++f4) yp[f4] = make_float4(out[s][f4 * 4], out[s][f4 * 4 + 1], out[s][f4 * 4 + 2], out[s][f4 * 4 + 3]);
+    }
+  }
 }
 
 // ---- conv_out_classes (mstcn.py:177): logits[c, t] = Wout[c,:] . h[t,:] + b[c]; channel-major output (coalesced over t).
@@ -210,7 +347,7 @@ struct sv_mstcn {
   bool packed = false;
   float* d_weights = nullptr;  // single device blob
   // offsets (in floats) into the blob
-  struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next; std::vector<size_t> layer; };
+  struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next, w_in_hi = 0, w_in_lo = 0; std::vector<size_t> layer; };
   std::vector<Stage> stages;
   int64_t launches = 0;
 };
@@ -241,18 +378,23 @@ int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n
   h->launches = 1;
   const float* W = h->d_weights;
   const size_t layer_smem = (3 * F * F + F * F + 2 * F) * sizeof(float);
-  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_layer_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(layer_smem)));
+  constexpr int NS = 1;  // time steps per thread in the layer kernel (NS = 2 measured slower on B200: 167 registers, 92 vs 76 us)
+  const unsigned lb = static_cast<unsigned>(ceil_div64(ceil_div64(T, NS), 128));
+  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_layer_kernel<F, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(layer_smem)));
   float* cur = bufA;  // current stage input / running activation
   float* nxt = bufB;
   for (int s = 0; s < c.stages; ++s) {
     const sv_mstcn::Stage& S = h->stages[s];
     if (s == 0) {
-      mstcn_inproj_kernel<F><<<static_cast<unsigned>(ceil_div64(T, 64)), 256, 0, st>>>(feats, W + S.w_in, W + S.b_in, T, c.f_dim, cur);
-      SV_TRY(launch_status("mstcn_inproj_kernel"));
+      constexpr size_t inproj_smem = (3 * 128 * (32 + 4) + 2 * 3 * 32 * (F + 8)) * sizeof(float);
+      SV_CUDA_OK(cudaFuncSetAttribute(mstcn_inproj_tf32x3_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inproj_smem)));
+      mstcn_inproj_tf32x3_kernel<F><<<static_cast<unsigned>(ceil_div64(T, 128)), 128, inproj_smem, st>>>(feats, W + S.w_in_hi, W + S.w_in_lo, W + S.b_in, T,
+                                                                                                         c.f_dim, cur);
+      SV_TRY(launch_status("mstcn_inproj_tf32x3_kernel"));
       ++h->launches;
     }
     for (int l = 0; l < c.layers; ++l) {
-      mstcn_layer_kernel<F><<<tb, 128, layer_smem, st>>>(cur, frame_start, W + S.layer[l], 1 << l, T, nxt);
+      mstcn_layer_kernel<F, NS><<<lb, 128, layer_smem, st>>>(cur, frame_start, W + S.layer[l], 1 << l, T, nxt);
       SV_TRY(launch_status("mstcn_layer_kernel"));
       ++h->launches;
       std::swap(cur, nxt);
@@ -330,6 +472,24 @@ int sv_mstcn_pack_weights(sv_mstcn_handle* h) {
       for (int64_t d = 0; d < dim; ++d) blob[S.w_in + d * F + f] = w->data[f * dim + d];
     S.b_in = reserve(F);
     std::copy(b->data.begin(), b->data.end(), blob.begin() + S.b_in);
+    if (s == 0) {  // TF32 hi/lo split of the stage-1 projection for the 3xTF32 tensor-core kernel
+      auto tf32_rna = [](float x) {
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;  // round to nearest (ties away) at 10 mantissa bits, like cvt.rna.tf32.f32
+        float r;
+        memcpy(&r, &u, 4);
+        return r;
+      };
+      S.w_in_hi = reserve(dim * F);
+      S.w_in_lo = reserve(dim * F);
+      for (int64_t i = 0; i < dim * F; ++i) {
+        const float x = blob[S.w_in + i];
+        const float hi = tf32_rna(x);
+        blob[S.w_in_hi + i] = hi;
+        blob[S.w_in_lo + i] = tf32_rna(x - hi);
+      }
+    }
     for (int l = 0; l < c.layers; ++l) {
       const std::string lp = p + ".layers." + std::to_string(l);
       const HostTensor *wd, *bd, *w1, *b1;
