@@ -105,12 +105,6 @@ __device__ __forceinline__ f32x2 f2_gelu_erf_poly(f32x2 x) {
 #undef SV_C2
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_GELU) return gelu_erf(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  return v;
-}
-
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -347,15 +347,6 @@ __global__ void __launch_bounds__(256) bf16_to_f32_kernel(const bf16* __restrict
   if (idx < n) out[idx] = __bfloat162float(x[idx]);
 }
 
-__global__ void __launch_bounds__(256) copy_bf16_strided_kernel(const bf16* __restrict__ x, int64_t rows, int C, bf16* __restrict__ out, int64_t ldo) {
-  const int cv = C >> 3;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= rows * cv) return;
-  const int c8 = static_cast<int>(idx % cv);
-  const int64_t r = idx / cv;
-  *reinterpret_cast<uint4*>(out + r * ldo + c8 * 8) = __ldg(reinterpret_cast<const uint4*>(x + r * C + c8 * 8));
-}
-
 inline unsigned blocks_for(int64_t total) { return static_cast<unsigned>(ceil_div64(total, 256)); }
 
 }  // namespace
@@ -440,12 +431,6 @@ int launch_token_mean(const float* x, int B, int tokens, int C, float* out, cuda
 int launch_bf16_to_f32(const bf16* x, float* out, int64_t n, cudaStream_t st) {
   bf16_to_f32_kernel<<<blocks_for(n), 256, 0, st>>>(x, out, n);
   return launch_status("bf16_to_f32_kernel");
-}
-
-int launch_copy_bf16_strided(const bf16* x, int64_t rows, int C, bf16* out, int64_t ldo, cudaStream_t st) {
-  SV_CHECK(C % 8 == 0 && ldo % 8 == 0, "strided copy needs C%8==0");
-  copy_bf16_strided_kernel<<<blocks_for(rows * (C / 8)), 256, 0, st>>>(x, rows, C, out, ldo);
-  return launch_status("copy_bf16_strided_kernel");
 }
 
 }  // namespace sv

@@ -16,7 +16,6 @@ int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaSt
 int launch_bilinear_tokens(const bf16* x, int B, int H, int W, int C, int Ho, int Wo, bf16* out, int64_t ldo, cudaStream_t st);
 int launch_token_mean(const float* x, int B, int tokens, int C, float* out, cudaStream_t st);
 int launch_bf16_to_f32(const bf16* x, float* out, int64_t n, cudaStream_t st);
-int launch_copy_bf16_strided(const bf16* x, int64_t rows, int C, bf16* out, int64_t ldo, cudaStream_t st);
 int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B,
                      int heads, int Nq, int Nkv, int hd, float scale, cudaStream_t st);
 

@@ -16,66 +16,11 @@
 namespace sv {
 namespace {
 
-// ---- stage-1 input projection: out[t, f] = sum_d feats[t, d] * W[f, d] + b[f]   (conv_1x1, mstcn.py:174)
-// fp32 SIMT GEMM, CTA tile 64 x F, K-chunk 32.  HBM-bound in principle (8 KB read per frame, 16 FLOP/B).
-template <int F>
-__global__ void __launch_bounds__(256) mstcn_inproj_kernel(const float* __restrict__ feats, const float* __restrict__ Wt /*[D][F]*/,
-                                                           const float* __restrict__ bias, int64_t T, int D, float* __restrict__ out) {
-  constexpr int BM = 64, BK = 32;
-  constexpr int TN = 4;
-  constexpr int TM = BM * F / (256 * TN);  // F=32 -> 2, F=64 -> 4
-  constexpr int TX = F / TN;               // threads along f
-  __shared__ float As[BK][BM + 1];         // [k][row]
-  __shared__ __align__(16) float Ws[BK][F];  // [k][f]
-  const int tid = threadIdx.x;
-  const int tx = tid % TX, ty = tid / TX;
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-
-  for (int k0 = 0; k0 < D; k0 += BK) {
-    // A tile: 64 rows x 32 k  (512 float4, 2 per thread), coalesced along d
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int v = tid + i * 256;
-      const int r = v / (BK / 4), c4 = v % (BK / 4);
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < T) a = __ldg(reinterpret_cast<const float4*>(feats + (row0 + r) * D + k0 + c4 * 4));
-      As[c4 * 4 + 0][r] = a.x; As[c4 * 4 + 1][r] = a.y; As[c4 * 4 + 2][r] = a.z; As[c4 * 4 + 3][r] = a.w;
-    }
-    // W tile: 32 k x F
-    for (int v = tid; v < BK * F / 4; v += 256) {
-      const int kk = v / (F / 4), f4 = v % (F / 4);
-      *reinterpret_cast<float4*>(&Ws[kk][f4 * 4]) = __ldg(reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(k0 + kk) * F + f4 * 4));
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][tx * TN]);
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const float a = As[kk][ty * TM + i];
-        acc[i][0] = fmaf(a, w.x, acc[i][0]); acc[i][1] = fmaf(a, w.y, acc[i][1]);
-        acc[i][2] = fmaf(a, w.z, acc[i][2]); acc[i][3] = fmaf(a, w.w, acc[i][3]);
-      }
-    }
-    __syncthreads();
-  }
-  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + tx * TN));
-#pragma unroll
-  for (int i = 0; i < TM; ++i) {
-    const int64_t r = row0 + ty * TM + i;
-    if (r < T) *reinterpret_cast<float4*>(out + r * F + tx * TN) = make_float4(acc[i][0] + b.x, acc[i][1] + b.y, acc[i][2] + b.z, acc[i][3] + b.w);
-  }
-}
-
-// ---- stage-1 input projection on tensor cores with fp32-level accuracy ("3xTF32"): each fp32 operand is split into a TF32
+// ---- stage-1 input projection (conv_1x1, mstcn.py:174: out[t,f] = sum_d feats[t,d] W[f,d] + b[f]) on tensor cores with fp32-level
+// accuracy ("3xTF32"): each fp32 operand is split into a TF32
 // high part and a TF32 residual, and  x*w ~= xh*wh + xh*wl + xl*wh  (dropped term ~2^-22 relative), three mma.sync.m16n8k8.tf32
 // per tile step.  The 8 KB/frame feature read is the only HBM traffic, and with the arithmetic off the FP32 pipe the kernel
-// is bound by it (the SIMT version above needs 16 FLOP per byte from a 72 TFLOP/s pipe and is compute-bound at ~0.1 of HBM).
+// is bound by it (an fp32 SIMT GEMM needs 16 FLOP per byte from a 72 TFLOP/s pipe: measured 0.10 of the HBM peak, compute-bound).
 // feats tiles arrive through a 3-stage cp.async ring; W is pre-split on the host.
 __device__ __forceinline__ uint32_t to_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
