@@ -6,6 +6,8 @@
 // more HBM traffic than the image itself.  One CTA = one 8x8 tile of output pixels: the 35x35xCin input patch is staged in
 // shared memory (bf16), expanded there into the [64 x K] operand, multiplied on tensor cores (mma.sync m16n8k16 — the
 // contraction is 0.4 % of the path's FLOPs) and normalised / activated in registers before the only global writes.
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace sv {
@@ -186,12 +188,10 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
 template <int COUT>
 int stem_launch(const StemParams& p, cudaStream_t st) {
   constexpr size_t smem = (static_cast<size_t>(COUT) * kLdA + 64 * kLdA + 3 * kPatch * (kPatch + 5)) * sizeof(bf16);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(stem): ") + cudaGetErrorString(e));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(stem_conv_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); });
+  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(stem): ") + cudaGetErrorString(attr_err));
   const long long tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
   const int grid = static_cast<int>(std::min<long long>(tiles, 8LL * device_sm_count()));
   stem_conv_kernel<COUT><<<grid, 128, smem, st>>>(p);
