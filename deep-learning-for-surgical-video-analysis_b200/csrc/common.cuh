@@ -76,7 +76,8 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn
 // two bf16 packed in a 32-bit word -> fp32x2 (exact: bf16 is the top half of an fp32)
 __device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t v) {
   f32x2 r;
-  asm("{\n\t.reg .b32 lo, hi;\n\tshl.b32 lo, %1, 16;\n\tand.b32 hi, %1, 0xffff0000;\n\tmov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(v));
+  // prmt/and run on the integer ALU; a plain shift is often emitted as IMAD.U32, which competes with the FFMA2s for the FMA pipe
+  asm("{\n\t.reg .b32 lo, hi;\n\tprmt.b32 lo, %1, 0, 0x1044;\n\tand.b32 hi, %1, 0xffff0000;\n\tmov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(v));
   return r;
 }
 
@@ -102,6 +103,33 @@ __device__ __forceinline__ f32x2 f2_gelu_erf_poly(f32x2 x) {
   q = f2_fma(q, w, SV_C2(-6.634692395e-02f));
   q = f2_fma(q, w, SV_C2(3.989031282e-01f));
   return f2_fma(f2_mul(x, xc), q, f2_mul(x, SV_C2(0.5f)));
+#undef SV_C2
+}
+
+// Two independent GELU evaluations with their Horner chains interleaved step by step (the dependent FFMA2 chain of one
+// evaluation leaves issue slots empty; two side by side fill them).
+__device__ __forceinline__ void f2_gelu_erf_poly_x2(f32x2& xa, f32x2& xb) {
+  float a0, a1, b0, b1;
+  f2_unpack(xa, a0, a1);
+  f2_unpack(xb, b0, b1);
+  const float lim = 4.2426406871192851f;
+  const f32x2 ca = f2_pack(fminf(fmaxf(a0, -lim), lim), fminf(fmaxf(a1, -lim), lim));
+  const f32x2 cb = f2_pack(fminf(fmaxf(b0, -lim), lim), fminf(fmaxf(b1, -lim), lim));
+  const f32x2 wa = f2_mul(ca, ca), wb = f2_mul(cb, cb);
+#define SV_C2(v) f2_pack(v, v)
+  f32x2 qa = f2_fma(SV_C2(5.626770213e-11f), wa, SV_C2(-5.371870724e-09f));
+  f32x2 qb = f2_fma(SV_C2(5.626770213e-11f), wb, SV_C2(-5.371870724e-09f));
+#define SV_STEP(c) qa = f2_fma(qa, wa, SV_C2(c)); qb = f2_fma(qb, wb, SV_C2(c));
+  SV_STEP(2.268296714e-07f)
+  SV_STEP(-5.646215765e-06f)
+  SV_STEP(9.359063167e-05f)
+  SV_STEP(-1.109400333e-03f)
+  SV_STEP(9.818119241e-03f)
+  SV_STEP(-6.634692395e-02f)
+  SV_STEP(3.989031282e-01f)
+#undef SV_STEP
+  xa = f2_fma(f2_mul(xa, ca), qa, f2_mul(xa, SV_C2(0.5f)));
+  xb = f2_fma(f2_mul(xb, cb), qb, f2_mul(xb, SV_C2(0.5f)));
 #undef SV_C2
 }
 

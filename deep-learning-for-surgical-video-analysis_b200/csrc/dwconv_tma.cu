@@ -18,10 +18,12 @@ namespace {
 constexpr int kTW = 8;          // max output columns per tile (= consumer warps); 7 or 8 are used, whichever tiles W exactly
 constexpr int kTH = 7;          // output rows per tile
 constexpr int kCB = 128;        // channels per tile (32 lanes x 4)
-constexpr int kStages = 3;
+constexpr int kStages = 4;
+constexpr int kPrefetch = 2;      // tiles in flight ahead of the one being computed; < kStages - 1 so that the producer lane
+                                  // re-fills a stage released a whole tile ago and never waits for the slowest warp
 constexpr int kBoxW = kTW + 2, kBoxH = kTH + 2;
 constexpr int kTileBytes = kBoxH * kBoxW * kCB * 2;  // 23 040
-constexpr int kThreads = 32 * (1 + kTW);
+constexpr int kThreads = 32 * kTW;  // 8 warps: 2 CTAs/SM -> 4 warps per scheduler -> 128 registers per thread available
 
 struct DwParams {
   const float* w9c;
@@ -31,7 +33,9 @@ struct DwParams {
   long long ldo;
   int tiles_x, tiles_y, cblks;
   int tw;  // output columns per tile actually used (<= kTW); box width = tw + 2
-  long long num_tiles;
+  int num_tiles;
+  int tiles_per_cblk;
+  long long row_stride;  // elements between vertically adjacent output pixels (W * ldo)
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -53,36 +57,51 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   }
   __syncthreads();
 
-  const long long tiles_per_cblk = static_cast<long long>(p.B) * p.tiles_y * p.tiles_x;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const int cblk = static_cast<int>(t / tiles_per_cblk);
-        long long r = t % tiles_per_cblk;
-        const int tx = static_cast<int>(r % p.tiles_x); r /= p.tiles_x;
-        const int ty = static_cast<int>(r % p.tiles_y);
-        const int b = static_cast<int>(r / p.tiles_y);
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        tile_coord[stage] = make_int4(cblk, tx, ty, b);  // visible to the consumers through the barrier's release/acquire
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBoxH * (p.tw + 2) * kCB * 2));
-        ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * p.tw - 1, ty * kTH - 1, b);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-      }
+  // Every warp is a consumer (warp -> output column, lane -> 4 channels); lane 0 of warp 0 additionally plays TMA
+  // producer, issuing the load of tile k+kPrefetch at the top of iteration k.  (A dedicated producer warp would make
+  // 9 warps per CTA = 5 on one scheduler at 2 CTAs/SM, capping the kernel at 96 registers; the consumer loop wants more.)
+  auto issue_tile = [&](int t, int stage, uint32_t phase) {
+    const int cblk = t / p.tiles_per_cblk;
+    int r = t - cblk * p.tiles_per_cblk;
+    const int per_b = p.tiles_y * p.tiles_x;
+    const int b = r / per_b;
+    r -= b * per_b;
+    const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+    tile_coord[stage] = make_int4(cblk, tx, ty, b);  // visible to the consumers through the barrier's release/acquire
+    ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBoxH * (p.tw + 2) * kCB * 2));
+    ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * p.tw - 1, ty * kTH - 1, b);
+  };
+  // each CTA walks one contiguous range of tiles: neighbouring tiles (shared halos) are loaded back to back and the
+  // 128-channel weight block in registers changes at most a couple of times per CTA
+  const int per_cta = p.num_tiles / static_cast<int>(gridDim.x), extra = p.num_tiles % static_cast<int>(gridDim.x);
+  const int t_begin = static_cast<int>(blockIdx.x) * per_cta + min(static_cast<int>(blockIdx.x), extra);
+  const int t_end = t_begin + per_cta + (static_cast<int>(blockIdx.x) < extra ? 1 : 0);
+  const bool is_producer = threadIdx.x == 0;
+  int pt = t_begin, pstage = 0;  // producer cursor
+  uint32_t pphase = 0;
+  if (is_producer) {
+    for (int i = 0; i < kPrefetch && pt < t_end; ++i, ++pt) {
+      issue_tile(pt, pstage, pphase);
+      if (++pstage == kStages) { pstage = 0; pphase ^= 1u; }
     }
-  } else if (warp - 1 < p.tw) {
-    // ------------------------------------------------------------ consumers: warp -> column, lane -> 4 channels
-    const int col = warp - 1;
-    const int boxw = p.tw + 2;
-    int stage = 0;
-    uint32_t phase = 0;
-    int cur_cblk = -1;
-    f32x2 wt[9][2];
-    f32x2 bias0 = 0, bias1 = 0;
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+  }
+  const int col = warp;
+  const bool active = col < p.tw;
+  const int boxw = p.tw + 2;
+  int stage = 0;
+  uint32_t phase = 0;
+  int cur_cblk = -1;
+  f32x2 wt[9][2];
+  f32x2 bias0 = 0, bias1 = 0;
+  for (int t = t_begin; t < t_end; ++t) {
+    if (is_producer && pt < t_end) {
+      issue_tile(pt, pstage, pphase);
+      ++pt;
+      if (++pstage == kStages) { pstage = 0; pphase ^= 1u; }
+    }
+    __syncwarp();
+    if (active) {
       ptx::mbar_wait(&full_bar[stage], phase);
       const int4 tc = tile_coord[stage];
       const int cblk = tc.x, tx = tc.y, ty = tc.z, b = tc.w;
@@ -101,12 +120,13 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       }
       const int w = tx * p.tw + col;
       const int h0 = ty * kTH;
-      // smem tile: [kBoxH][kBoxW][128 ch] bf16; this thread reads box columns col, col+1, col+2
+      // smem tile: [kBoxH][boxw][128 ch] bf16; this thread reads box columns col, col+1, col+2
       const uint2* tile = reinterpret_cast<const uint2*>(smem + stage * kTileBytes) + col * (kCB / 4) + lane;
+      const int row_words = boxw * (kCB / 4);
       auto load_row = [&](int br, f32x2 (&dst)[3][2]) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const uint2 v = tile[(br * boxw + dx) * (kCB / 4)];
+          const uint2 v = tile[br * row_words + dx * (kCB / 4)];
           dst[dx][0] = f2_from_bf16x2(v.x);
           dst[dx][1] = f2_from_bf16x2(v.y);
         }
@@ -114,8 +134,8 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       f32x2 ring[3][3][2];
       load_row(0, ring[0]);
       load_row(1, ring[1]);
-      bf16* obase = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.ldo + c0;
-      const bool col_ok = w < p.W;
+      bf16* optr = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.ldo + c0;
+      const int rows_ok = (w < p.W) ? min(kTH, p.H - h0) : 0;  // rows of this tile column that exist
 #pragma unroll
       for (int i = 0; i < kTH; ++i) {
         load_row(i + 2, ring[(i + 2) % 3]);
@@ -128,22 +148,20 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
             a1 = f2_fma(ring[(i + dy) % 3][dx][1], wt[dy * 3 + dx][1], a1);
           }
         }
-        a0 = f2_gelu_erf_poly(a0);
-        a1 = f2_gelu_erf_poly(a1);
+        f2_gelu_erf_poly_x2(a0, a1);
         float y0, y1, y2, y3;
         f2_unpack(a0, y0, y1);
         f2_unpack(a1, y2, y3);
-        if (col_ok && h0 + i < p.H) {
-          uint2 o;
-          o.x = pack_bf16x2(y0, y1);
-          o.y = pack_bf16x2(y2, y3);
-          *reinterpret_cast<uint2*>(obase + static_cast<long long>(i) * p.W * p.ldo) = o;
-        }
+        uint2 o;
+        o.x = pack_bf16x2(y0, y1);
+        o.y = pack_bf16x2(y2, y3);
+        if (i < rows_ok) *reinterpret_cast<uint2*>(optr) = o;
+        optr += p.row_stride;
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);  // this warp is done reading the stage
-      if (++stage == kStages) { stage = 0; phase ^= 1u; }
     }
+    if (++stage == kStages) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -195,7 +213,11 @@ int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tw = plan.tw;
   p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
-  p.num_tiles = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
+  const long long nt = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
+  if (nt >= (1LL << 31)) return fail(SV_ERR_INVALID, "dwconv: more than 2^31 tiles");
+  p.num_tiles = static_cast<int>(nt);
+  p.tiles_per_cblk = plan.B * p.tiles_y * p.tiles_x;
+  p.row_stride = static_cast<long long>(plan.W) * plan.ldo;
   const int sms = device_sm_count();
   const int grid = static_cast<int>(std::min<long long>(p.num_tiles, 2LL * sms));
   dwconv3x3_gelu_tma_kernel<<<grid, kThreads, smem_bytes, st>>>(plan.tmap, p);
