@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsurgvid.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "dwconv_tma.cu", "stem.cu", "mstcn.cu", "evp.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "dwconv_tma.cu", "stem.cu", "mstcn.cu", "evp.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 SV_OK = 0
@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "sv_mstcn_forward", "sv_mstcn_last_launch_count",
     "sv_op_gemm_bf16", "sv_op_layernorm", "sv_op_im2col", "sv_op_dwconv3x3_gelu", "sv_op_attention", "sv_op_gauss5x5",
     "sv_op_bilinear_tokens", "sv_op_token_mean", "sv_op_stem_conv",
+    "sv_prep_create", "sv_prep_destroy", "sv_prep_workspace_bytes", "sv_prep_images", "sv_prep_flow",
 ]
 
 
@@ -121,10 +122,16 @@ def _declare(lib):
     lib.sv_op_stem_conv.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]
     lib.sv_op_token_mean.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.sv_prep_create.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, f32p, f32p, POINTER(c_void_p)]
+    lib.sv_prep_destroy.argtypes = [c_void_p]
+    lib.sv_prep_workspace_bytes.argtypes = [c_void_p, c_int32]
+    lib.sv_prep_workspace_bytes.restype = c_size_t
+    lib.sv_prep_images.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sv_prep_flow.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("sv_last_error", "sv_evp_workspace_bytes", "sv_mstcn_workspace_bytes", "sv_evp_last_launch_count",
-                        "sv_mstcn_last_launch_count"):
+                        "sv_mstcn_last_launch_count", "sv_prep_workspace_bytes"):
             fn.restype = c_int32
 
 

@@ -109,6 +109,64 @@ class LFBExtractor:
         compute.synchronize()
         return out
 
+    @torch.no_grad()
+    def extract_raw(self, frames_u8: torch.Tensor, segmaps_u8: torch.Tensor, flow_raw: Optional[torch.Tensor], resize: int = 250,
+                    crop: int = 224, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Same as `extract`, but from what the reference's dataset class starts from after decoding:
+        frames/segmaps uint8 [N, H, W, 3] HOST, flow float32 [N, Hf, Wf, 2] HOST (raw RAFT field) or None.  The
+        Resize/CenterCrop/ToTensor/Normalize and the flow resize+rescale run on the GPU (preprocess.FramePreprocessor), so
+        uint8 frames cross PCIe instead of normalised fp32."""
+        from .preprocess import FramePreprocessor
+        N, H, W = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
+        fhw = None if flow_raw is None else (flow_raw.shape[1], flow_raw.shape[2])
+        key = (H, W, fhw, resize, crop)
+        if getattr(self, "_prep_key", None) != key:
+            self._prep = FramePreprocessor((H, W), flow_hw=fhw, resize=resize, crop=crop)
+            self._prep_key = key
+            self._raw = []
+            for _ in range(2):
+                fu = torch.empty((self.batch_size, H, W, 3), dtype=torch.uint8, device=self.device)
+                su = torch.empty((self.batch_size, H, W, 3), dtype=torch.uint8, device=self.device)
+                fl = None if fhw is None else torch.empty((self.batch_size, fhw[0], fhw[1], 2), dtype=torch.float32, device=self.device)
+                self._raw.append((fu, su, fl, torch.cuda.Event(), torch.cuda.Event()))
+            self._pre_out = (torch.empty((self.batch_size, 3, crop, crop), dtype=torch.float32, device=self.device),
+                             torch.empty((self.batch_size, 3, crop, crop), dtype=torch.float32, device=self.device),
+                             None if fhw is None else torch.empty((self.batch_size, 2, crop, crop), dtype=torch.float32, device=self.device))
+        if out is None:
+            out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
+        compute = torch.cuda.current_stream(self.device)
+        self.h2d_bytes = self.d2h_bytes = 0
+        starts, b0, ramp = [], 0, max(1, self.batch_size // 4)
+        while b0 < N:
+            n = min(ramp, self.batch_size, N - b0)
+            starts.append((b0, n))
+            b0 += n
+            ramp *= 2
+        x, s, f = self._pre_out
+        for bi, (b0, n) in enumerate(starts):
+            fu, su, fl, ev_in, ev_free = self._raw[bi % 2]
+            with torch.cuda.stream(self._copy_stream):
+                if bi >= 2:
+                    self._copy_stream.wait_event(ev_free)
+                fu[:n].copy_(frames_u8[b0:b0 + n], non_blocking=True)
+                su[:n].copy_(segmaps_u8[b0:b0 + n], non_blocking=True)
+                self.h2d_bytes += 2 * n * H * W * 3
+                if fl is not None:
+                    fl[:n].copy_(flow_raw[b0:b0 + n], non_blocking=True)
+                    self.h2d_bytes += n * fhw[0] * fhw[1] * 2 * 4
+                ev_in.record(self._copy_stream)
+            compute.wait_event(ev_in)
+            self._prep.images(fu[:n], out=x[:n])
+            self._prep.images(su[:n], out=s[:n])
+            if fl is not None:
+                self._prep.flow(fl[:n], out=f[:n])
+            ev_free.record(compute)  # the raw staging buffers are free once the transforms have run
+            feats = self.model(x[:n], s[:n], None if fl is None else f[:n], return_features=True)
+            out[b0:b0 + n].copy_(feats, non_blocking=True)
+            self.d2h_bytes += n * self.model.embedding_dim * 4
+        compute.synchronize()
+        return out
+
     def extract_float64(self, frames, segmaps, flow) -> np.ndarray:
         """Same values as `extract`, as the float64 ndarray the reference pickles (generate_evp_LFB.py:513-520)."""
         return self.extract(frames, segmaps, flow).numpy().astype(np.float64)

@@ -191,6 +191,26 @@ int sv_op_stem_conv(const float* src, const uint16_t* w, int32_t ldw, const floa
 /* mean over `tokens` consecutive rows of fp32 [B*tokens, C] -> [B, C] (AdaptiveAvgPool2d(1), segformer_head.py:167). */
 int sv_op_token_mean(const float* x, int32_t B, int32_t tokens, int32_t C, float* out, void* stream);
 
+/* ---- on-GPU input transforms: the reference's per-frame dataset transforms, applied to device copies of
+ * the raw uint8 frames / float32 RAFT flow instead of on the CPU inside CholecFlowDataset.__getitem__ (data_process.py:409-483).
+ * A handle fixes the geometry and owns the coefficient tables; buffers and the workspace belong to the caller. */
+typedef struct sv_prep sv_prep;
+
+/* in_h x in_w: size of the uint8 RGB frames / segmentation maps; flow_h x flow_w: size of the raw flow field (0, 0 = no flow);
+ * resize, crop: transforms.Resize((resize, resize)) then CenterCrop(crop) (generate_evp_LFB.py:243-245; 250 and 224);
+ * mean3/std3: transforms.Normalize constants (generate_evp_LFB.py:247). */
+int sv_prep_create(int32_t in_h, int32_t in_w, int32_t flow_h, int32_t flow_w, int32_t resize, int32_t crop, const float* mean3,
+                   const float* std3, sv_prep** out);
+int sv_prep_destroy(sv_prep* h);
+/* bytes of device scratch sv_prep_images needs for B frames (uint8 intermediate between Pillow's two resampling passes) */
+size_t sv_prep_workspace_bytes(const sv_prep* h, int32_t B);
+/* src: uint8 [B, in_h, in_w, 3] (HWC, RGB) -> out: float32 [B, 3, crop, crop]:
+ * Resize (Pillow antialiased bilinear, bit-exact) -> CenterCrop -> ToTensor -> Normalize (generate_evp_LFB.py:242-248). */
+int sv_prep_images(sv_prep* h, const uint8_t* src, int32_t B, float* out, void* workspace, size_t workspace_bytes, void* stream);
+/* flow: float32 [B, flow_h, flow_w, 2] -> out: float32 [B, 2, crop, crop]: cv2.resize(INTER_LINEAR) to (resize, resize),
+ * u *= resize/flow_w, v *= resize/flow_h, CenterCrop (data_process.py:432-447, 461-480). */
+int sv_prep_flow(sv_prep* h, const float* flow, int32_t B, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
