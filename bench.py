@@ -268,6 +268,34 @@ def run_ours(args):
                "h2d_bytes_per_step": int(ext.h2d_bytes + T * 2048 * 4), "d2h_bytes_per_step": int(ext.d2h_bytes + logits_h.numel() * 4),
                "steps": e2e_steps, "api": "LFBExtractor.extract(model=mit_b3_evp drop-in) + MultiStageModel_S.forward_videos"}
         del xh, sh, fh
+        # same call chain from what the reference's dataset class holds after JPEG decode: uint8 250x250 frames and
+        # segmentation maps + the raw fp32 RAFT field; Resize/CenterCrop/ToTensor/Normalize and the flow resize run on the GPU
+        g = torch.Generator().manual_seed(11 + rank)
+        fr_u8 = torch.randint(0, 256, (T, 250, 250, 3), dtype=torch.uint8, generator=g).pin_memory()
+        sg_u8 = ((torch.rand((T, 250, 250, 1), generator=g) > 0.7).to(torch.uint8) * 255).expand(T, 250, 250, 3).contiguous().pin_memory()
+        fl_raw = (2.0 * torch.randn((T, 250, 250, 2), generator=g)).pin_memory()
+
+        @torch.no_grad()
+        def e2e_raw_step():
+            f_h = ext.extract_raw(fr_u8, sg_u8, fl_raw, out=out_h)
+            lg = tcn.forward_videos(f_h.to(dev, non_blocking=True), [T])
+            logits_h.copy_(lg, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_raw_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_raw_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e["from_uint8_frames"] = {"value": world * T * e2e_steps / float(dt.item()), "unit": "frames/s",
+                                    "h2d_bytes_per_step": int(ext.h2d_bytes + T * 2048 * 4),
+                                    "d2h_bytes_per_step": int(ext.d2h_bytes + logits_h.numel() * 4), "steps": e2e_steps,
+                                    "api": "LFBExtractor.extract_raw(uint8 250x250 frames + segmaps, fp32 250x250 flow) + MultiStageModel_S.forward_videos"}
+        del fr_u8, sg_u8, fl_raw
 
     # ---- per-kernel-class device timing (CUDA events around every launch, on the launching stream; untimed extra pass)
     roofline, classes = None, None
