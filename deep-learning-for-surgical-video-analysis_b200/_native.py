@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "sv_evp_create", "sv_evp_destroy", "sv_evp_set_tensor", "sv_evp_pack_weights", "sv_evp_workspace_bytes",
     "sv_evp_forward", "sv_evp_classify", "sv_evp_read_tap", "sv_evp_last_launch_count", "sv_evp_set_profile", "sv_evp_get_profile", "sv_evp_dump_profile",
     "sv_mstcn_create", "sv_mstcn_destroy", "sv_mstcn_set_tensor", "sv_mstcn_pack_weights", "sv_mstcn_workspace_bytes",
-    "sv_mstcn_forward", "sv_mstcn_last_launch_count",
+    "sv_mstcn_forward", "sv_mstcn_last_launch_count", "sv_mstcn_forward_query", "sv_op_causal_windows",
     "sv_op_gemm_bf16", "sv_op_layernorm", "sv_op_im2col", "sv_op_dwconv3x3_gelu", "sv_op_attention", "sv_op_gauss5x5",
     "sv_op_bilinear_tokens", "sv_op_token_mean", "sv_op_stem_conv",
     "sv_prep_create", "sv_prep_destroy", "sv_prep_workspace_bytes", "sv_prep_images", "sv_prep_flow",
@@ -109,6 +109,8 @@ def _declare(lib):
     lib.sv_mstcn_workspace_bytes.restype = c_size_t
     lib.sv_mstcn_forward.argtypes = [c_void_p, c_void_p, i64p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.sv_mstcn_last_launch_count.argtypes = [c_void_p]
+    lib.sv_mstcn_forward_query.argtypes = [c_void_p, c_void_p, i64p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.sv_op_causal_windows.argtypes = [c_void_p, c_int64, c_int32, i64p, c_int32, c_int32, c_void_p, c_void_p]
     lib.sv_mstcn_last_launch_count.restype = c_int64
     lib.sv_op_gemm_bf16.argtypes = [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int64,
                                     c_void_p, c_int64, c_int32, c_void_p]

@@ -34,12 +34,16 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bo
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
 
-template <int F>
+// Q = 16 appends the Trans-SVNet query head to the same pass over the features: columns F..F+Q-1 of the packed weight hold
+// `Transformer.fc.weight` (Linear(f_dim, out_features, bias=False), adapter_transformer.py:325) and the epilogue writes
+// query[t, c] = tanh(feats[t] . fc[c]) (adapter_transformer.py:348) for c < q_out.
+template <int F, int Q>
 __global__ void __launch_bounds__(128) mstcn_inproj_tf32x3_kernel(const float* __restrict__ feats, const float* __restrict__ Whi,
                                                                   const float* __restrict__ Wlo, const float* __restrict__ bias, int64_t T, int D,
-                                                                  float* __restrict__ out) {
-  constexpr int BM = 128, BK = 32, ST = 3, NT = F / 8, MT = 2;   // each warp: 2 m16 tiles (32 rows) x F columns
-  constexpr int LDA = BK + 4, LDW = F + 8;  // conflict-free fragment loads
+                                                                  float* __restrict__ out, float* __restrict__ query, int q_out) {
+  constexpr int FW = F + Q;
+  constexpr int BM = 128, BK = 32, ST = 3, NT = FW / 8, MT = 2;   // each warp: 2 m16 tiles (32 rows) x FW columns
+  constexpr int LDA = BK + 4, LDW = FW + 8;  // conflict-free fragment loads
   extern __shared__ __align__(16) float sm[];
   float* As = sm;                       // [ST][BM][LDA]
   float* Wh = As + ST * BM * LDA;       // [ST][BK][LDW]
@@ -55,10 +59,10 @@ __global__ void __launch_bounds__(128) mstcn_inproj_tf32x3_kernel(const float* _
       const bool ok = row0 + r < T;
       cp_async_16(As + (stg * BM + r) * LDA + c4 * 4, ok ? feats + (row0 + r) * D + k0 + c4 * 4 : feats, ok);
     }
-    for (int i = tid; i < BK * (F / 4); i += 128) {       // 32 k x F/4 chunks, hi and lo
-      const int kk = i / (F / 4), f4 = i % (F / 4);
-      cp_async_16(Wh + (stg * BK + kk) * LDW + f4 * 4, Whi + static_cast<int64_t>(k0 + kk) * F + f4 * 4, true);
-      cp_async_16(Wl + (stg * BK + kk) * LDW + f4 * 4, Wlo + static_cast<int64_t>(k0 + kk) * F + f4 * 4, true);
+    for (int i = tid; i < BK * (FW / 4); i += 128) {      // 32 k x FW/4 chunks, hi and lo
+      const int kk = i / (FW / 4), f4 = i % (FW / 4);
+      cp_async_16(Wh + (stg * BK + kk) * LDW + f4 * 4, Whi + static_cast<int64_t>(k0 + kk) * FW + f4 * 4, true);
+      cp_async_16(Wl + (stg * BK + kk) * LDW + f4 * 4, Wlo + static_cast<int64_t>(k0 + kk) * FW + f4 * 4, true);
     }
   };
   float acc[MT][NT][4];
@@ -111,10 +115,21 @@ __global__ void __launch_bounds__(128) mstcn_inproj_tf32x3_kernel(const float* _
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
       const int col = nt * 8 + t * 2;
-      const float2 b = __ldg(reinterpret_cast<const float2*>(bias + col));
       const int64_t r0 = row0 + warp * 32 + m * 16 + g, r1 = r0 + 8;
-      if (r0 < T) *reinterpret_cast<float2*>(out + r0 * F + col) = make_float2(acc[m][nt][0] + b.x, acc[m][nt][1] + b.y);
-      if (r1 < T) *reinterpret_cast<float2*>(out + r1 * F + col) = make_float2(acc[m][nt][2] + b.x, acc[m][nt][3] + b.y);
+      if (col < F) {
+        const float2 b = __ldg(reinterpret_cast<const float2*>(bias + col));
+        if (r0 < T) *reinterpret_cast<float2*>(out + r0 * F + col) = make_float2(acc[m][nt][0] + b.x, acc[m][nt][1] + b.y);
+        if (r1 < T) *reinterpret_cast<float2*>(out + r1 * F + col) = make_float2(acc[m][nt][2] + b.x, acc[m][nt][3] + b.y);
+      } else if (query != nullptr) {
+        const int c = col - F;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (c + j < q_out) {
+            if (r0 < T) query[r0 * q_out + c + j] = tanhf(acc[m][nt][j]);
+            if (r1 < T) query[r1 * q_out + c + j] = tanhf(acc[m][nt][2 + j]);
+          }
+        }
+      }
     }
   }
 }
@@ -266,6 +281,20 @@ __global__ void __launch_bounds__(128) mstcn_out_kernel(const float* __restrict_
   for (int f4 = 0; f4 < F / 4; ++f4) np[f4] = make_float4(o[f4 * 4], o[f4 * 4 + 1], o[f4 * 4 + 2], o[f4 * 4 + 3]);
 }
 
+// out[t][j][c] = x[c][t - (len_q - 1) + j] (zero where the index is negative): the 30-frame causal windows of the MS-TCN logits that
+// Transformer.original_forward builds with a Python loop (adapter_transformer.py:335-343), for one video.
+__global__ void causal_windows_kernel(const float* __restrict__ x, int64_t ldx, int C, int64_t T, int len_q, float* __restrict__ out) {
+  const int64_t total = T * len_q * C;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int64_t r = i / C;
+    const int j = static_cast<int>(r % len_q);
+    const int64_t t = r / len_q;
+    const int64_t src = t - (len_q - 1) + j;
+    out[i] = src >= 0 ? __ldg(x + static_cast<int64_t>(c) * ldx + src) : 0.f;
+  }
+}
+
 __global__ void frame_start_kernel(const int64_t* __restrict__ offsets, int n_videos, int64_t T, int* __restrict__ frame_start) {
   const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= T) return;
@@ -294,6 +323,7 @@ struct sv_mstcn {
   // offsets (in floats) into the blob
   struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next, w_in_hi = 0, w_in_lo = 0; std::vector<size_t> layer; };
   std::vector<Stage> stages;
+  int q_out = 0;  // rows of the optional query head `fc.weight` packed next to the stage-1 projection (0 = absent)
   int64_t launches = 0;
 };
 
@@ -310,8 +340,22 @@ int expect(const sv_mstcn* h, const std::string& key, std::initializer_list<int6
   return SV_OK;
 }
 
+constexpr int kQCols = 16;  // query-head columns appended to the stage-1 projection (out_features <= 16)
+
+template <int F, int Q>
+int launch_inproj(sv_mstcn* h, const float* feats, int64_t T, float* out, float* query, cudaStream_t st) {
+  const sv_mstcn::Stage& S = h->stages[0];
+  const float* W = h->d_weights;
+  constexpr size_t smem = (3 * 128 * (32 + 4) + 2 * 3 * 32 * (F + Q + 8)) * sizeof(float);
+  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_inproj_tf32x3_kernel<F, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  mstcn_inproj_tf32x3_kernel<F, Q><<<static_cast<unsigned>(ceil_div64(T, 128)), 128, smem, st>>>(feats, W + S.w_in_hi, W + S.w_in_lo, W + S.b_in, T,
+                                                                                                 h->cfg.f_dim, out, query, h->q_out);
+  return launch_status("mstcn_inproj_tf32x3_kernel");
+}
+
 template <int F>
-int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n_videos, int64_t T, float* logits, void* ws, cudaStream_t st) {
+int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n_videos, int64_t T, float* logits, float* query, void* ws,
+                cudaStream_t st) {
   const sv_mstcn_cfg& c = h->cfg;
   char* p = static_cast<char*>(ws);
   float* bufA = reinterpret_cast<float*>(p);
@@ -331,11 +375,8 @@ int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n
   for (int s = 0; s < c.stages; ++s) {
     const sv_mstcn::Stage& S = h->stages[s];
     if (s == 0) {
-      constexpr size_t inproj_smem = (3 * 128 * (32 + 4) + 2 * 3 * 32 * (F + 8)) * sizeof(float);
-      SV_CUDA_OK(cudaFuncSetAttribute(mstcn_inproj_tf32x3_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(inproj_smem)));
-      mstcn_inproj_tf32x3_kernel<F><<<static_cast<unsigned>(ceil_div64(T, 128)), 128, inproj_smem, st>>>(feats, W + S.w_in_hi, W + S.w_in_lo, W + S.b_in, T,
-                                                                                                         c.f_dim, cur);
-      SV_TRY(launch_status("mstcn_inproj_tf32x3_kernel"));
+      if (h->q_out > 0) SV_TRY((launch_inproj<F, kQCols>(h, feats, T, cur, query, st)));
+      else SV_TRY((launch_inproj<F, 0>(h, feats, T, cur, nullptr, st)));
       ++h->launches;
     }
     for (int l = 0; l < c.layers; ++l) {
@@ -426,13 +467,28 @@ int sv_mstcn_pack_weights(sv_mstcn_handle* h) {
         memcpy(&r, &u, 4);
         return r;
       };
-      S.w_in_hi = reserve(dim * F);
-      S.w_in_lo = reserve(dim * F);
-      for (int64_t i = 0; i < dim * F; ++i) {
-        const float x = blob[S.w_in + i];
-        const float hi = tf32_rna(x);
-        blob[S.w_in_hi + i] = hi;
-        blob[S.w_in_lo + i] = tf32_rna(x - hi);
+      // optional query head of the Trans-SVNet wrapper: `fc.weight` [out_q, f_dim], no bias (adapter_transformer.py:325)
+      h->q_out = 0;
+      const HostTensor* fc = nullptr;
+      auto fit = h->tensors.find("fc.weight");
+      if (fit != h->tensors.end()) {
+        fc = &fit->second;
+        if (fc->shape.size() != 2 || fc->shape[1] != dim || fc->shape[0] < 1 || fc->shape[0] > kQCols)
+          return fail(SV_ERR_INVALID, "mstcn: 'fc.weight' must be [out_features <= 16, f_dim]");
+        h->q_out = static_cast<int>(fc->shape[0]);
+      }
+      const int64_t FW = F + (fc ? kQCols : 0);
+      S.w_in_hi = reserve(dim * FW);
+      S.w_in_lo = reserve(dim * FW);
+      for (int64_t d = 0; d < dim; ++d) {
+        for (int64_t f = 0; f < FW; ++f) {
+          float x = 0.f;
+          if (f < F) x = blob[S.w_in + d * F + f];
+          else if (f - F < h->q_out) x = fc->data[(f - F) * dim + d];
+          const float hi = tf32_rna(x);
+          blob[S.w_in_hi + d * FW + f] = hi;
+          blob[S.w_in_lo + d * FW + f] = tf32_rna(x - hi);
+        }
       }
     }
     for (int l = 0; l < c.layers; ++l) {
@@ -482,9 +538,15 @@ size_t sv_mstcn_workspace_bytes(const sv_mstcn_handle* h, int64_t total_frames) 
 
 int sv_mstcn_forward(sv_mstcn_handle* h, const float* feats, const int64_t* video_offsets, int32_t n_videos, float* logits,
                      void* workspace, size_t workspace_bytes, void* stream) {
+  return sv_mstcn_forward_query(h, feats, video_offsets, n_videos, logits, nullptr, workspace, workspace_bytes, stream);
+}
+
+int sv_mstcn_forward_query(sv_mstcn_handle* h, const float* feats, const int64_t* video_offsets, int32_t n_videos, float* logits, float* query,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   using namespace sv;
   SV_CHECK(h && feats && video_offsets && logits && workspace, "null argument");
   if (!h->packed) return fail(SV_ERR_STATE, "mstcn: pack_weights() has not been called");
+  if (query != nullptr && h->q_out == 0) return fail(SV_ERR_STATE, "mstcn: a query output was requested but no 'fc.weight' tensor was set");
   SV_CHECK(n_videos >= 1 && n_videos < 4096, "mstcn: 1 <= n_videos < 4096");
   SV_CHECK(video_offsets[0] == 0, "mstcn: video_offsets[0] must be 0");
   for (int i = 0; i < n_videos; ++i) SV_CHECK(video_offsets[i + 1] > video_offsets[i], "mstcn: empty video / non-increasing offsets");
@@ -498,8 +560,25 @@ int sv_mstcn_forward(sv_mstcn_handle* h, const float* feats, const int64_t* vide
   tail = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(tail) + 255) & ~static_cast<uintptr_t>(255));
   int64_t* d_offsets = reinterpret_cast<int64_t*>(tail);
   SV_CUDA_OK(cudaMemcpyAsync(d_offsets, video_offsets, (n_videos + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  if (h->cfg.f_maps == 32) return run_forward<32>(h, feats, d_offsets, n_videos, T, logits, workspace, st);
-  return run_forward<64>(h, feats, d_offsets, n_videos, T, logits, workspace, st);
+  if (h->cfg.f_maps == 32) return run_forward<32>(h, feats, d_offsets, n_videos, T, logits, query, workspace, st);
+  return run_forward<64>(h, feats, d_offsets, n_videos, T, logits, query, workspace, st);
+}
+
+int sv_op_causal_windows(const float* x, int64_t ldx, int32_t C, const int64_t* video_offsets, int32_t n_videos, int32_t len_q, float* out,
+                         void* stream) {
+  using namespace sv;
+  SV_CHECK(x && video_offsets && out, "null argument");
+  SV_CHECK(C >= 1 && len_q >= 1 && n_videos >= 1, "causal_windows: C, len_q, n_videos >= 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int v = 0; v < n_videos; ++v) {
+    const int64_t t0 = video_offsets[v], Tv = video_offsets[v + 1] - t0;
+    SV_CHECK(Tv > 0, "causal_windows: empty video");
+    const int64_t total = Tv * len_q * C;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(device_sm_count()) * 16));
+    causal_windows_kernel<<<blocks, 256, 0, st>>>(x + t0, ldx, C, Tv, len_q, out + t0 * len_q * C);
+    SV_TRY(launch_status("causal_windows_kernel"));
+  }
+  return SV_OK;
 }
 
 int64_t sv_mstcn_last_launch_count(const sv_mstcn_handle* h) { return h ? h->launches : 0; }

@@ -56,6 +56,7 @@ class MultiStageModel_S(nn.Module):
         self.smoothing = False
         self._native = {}
         self._weights_epoch = 0
+        self._fc_weight = None  # optional Trans-SVNet query head packed next to the stage-1 projection (set_query_head)
 
     # ------------------------------------------------------------------ native plumbing
     def _apply(self, fn, *args, **kwargs):
@@ -67,6 +68,22 @@ class MultiStageModel_S(nn.Module):
         return super().load_state_dict(*args, **kwargs)
 
     def refresh_weights(self):
+        self._weights_epoch += 1
+
+    def set_query_head(self, fc_weight):
+        """Attach `Transformer.fc.weight` ([out_features, f_dim], no bias; adapter_transformer.py:325) so that
+        `forward_videos_query` also returns tanh(fc(features)) from the same pass over the features.  None detaches it."""
+        if fc_weight is not None:
+            fc_weight = fc_weight.detach().to("cpu", torch.float32).contiguous()
+            if fc_weight.dim() != 2 or fc_weight.shape[1] != self.dim or not (1 <= fc_weight.shape[0] <= 16):
+                raise ValueError(f"fc weight must be [<=16, {self.dim}], got {tuple(fc_weight.shape)}")
+        self._fc_weight = fc_weight
+        # the native handle keeps tensors by name: rebuild it so that a detached head really disappears
+        for st in self._native.values():
+            if st.get("id") is not None:
+                ops.unregister_handle(st["id"])
+            _native.lib().sv_mstcn_destroy(st["handle"])
+        self._native = {}
         self._weights_epoch += 1
 
     def _state(self, device: torch.device):
@@ -86,13 +103,17 @@ class MultiStageModel_S(nn.Module):
                 a = np.ascontiguousarray(t.detach().to("cpu", torch.float32).numpy())
                 shape = (ctypes.c_int64 * max(a.ndim, 1))(*a.shape)
                 _native.check(lib.sv_mstcn_set_tensor(st["handle"], name.encode(), a.ctypes.data_as(ctypes.c_void_p), shape, a.ndim), "sv_mstcn_set_tensor")
+            if self._fc_weight is not None:
+                a = self._fc_weight.numpy()
+                shape = (ctypes.c_int64 * 2)(*a.shape)
+                _native.check(lib.sv_mstcn_set_tensor(st["handle"], b"fc.weight", a.ctypes.data_as(ctypes.c_void_p), shape, 2), "sv_mstcn_set_tensor")
             _native.check(lib.sv_mstcn_pack_weights(st["handle"]), "sv_mstcn_pack_weights")
         st["stamp"] = self._weights_epoch
         if st["id"] is None:
             st["id"] = ops.register_handle(_MstcnOpOwner(self, idx))
         return st
 
-    def _native_forward(self, idx: int, feats: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
+    def _native_forward(self, idx: int, feats: torch.Tensor, offsets: torch.Tensor, want_query: bool = False):
         st = self._native[idx]
         lib = _native.lib()
         T = feats.shape[0]
@@ -103,11 +124,17 @@ class MultiStageModel_S(nn.Module):
             st["workspace"] = ws
         out = torch.empty((self.num_stages, self.num_classes, T), dtype=torch.float32, device=feats.device)
         off = np.ascontiguousarray(offsets.detach().cpu().numpy().astype(np.int64))
-        rc = lib.sv_mstcn_forward(st["handle"], ctypes.c_void_p(feats.data_ptr()), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(off) - 1,
-                                  ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(),
-                                  ctypes.c_void_p(torch.cuda.current_stream(feats.device).cuda_stream))
-        _native.check(rc, "sv_mstcn_forward")
-        return out
+        query = None
+        if want_query:
+            if self._fc_weight is None:
+                raise RuntimeError("no query head attached: call set_query_head(fc_weight) first")
+            query = torch.empty((T, self._fc_weight.shape[0]), dtype=torch.float32, device=feats.device)
+        rc = lib.sv_mstcn_forward_query(st["handle"], ctypes.c_void_p(feats.data_ptr()), off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                        len(off) - 1, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(0 if query is None else query.data_ptr()),
+                                        ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                        ctypes.c_void_p(torch.cuda.current_stream(feats.device).cuda_stream))
+        _native.check(rc, "sv_mstcn_forward_query")
+        return (out, query) if want_query else out
 
     def last_launch_count(self, device=None) -> int:
         idx = torch.cuda.current_device() if device is None else torch.device(device).index
@@ -131,6 +158,18 @@ class MultiStageModel_S(nn.Module):
             raise ValueError("sum(lengths) must equal feats.shape[0]")
         st = self._state(feats.device)
         return torch.ops.surgvid.mstcn_forward(feats, offsets, st["id"])
+
+    def forward_videos_query(self, feats: torch.Tensor, lengths: Sequence[int]):
+        """`forward_videos` plus the Trans-SVNet decoder query tanh(fc(feats)) [sum(lengths), out_features]
+        (adapter_transformer.py:348), both from one pass over `feats`.  Needs `set_query_head`."""
+        self._check(feats)
+        feats = feats.to(torch.float32).contiguous()
+        offsets = torch.zeros(len(lengths) + 1, dtype=torch.int64)
+        offsets[1:] = torch.cumsum(torch.as_tensor(list(lengths), dtype=torch.int64), 0)
+        if int(offsets[-1]) != feats.shape[0]:
+            raise ValueError("sum(lengths) must equal feats.shape[0]")
+        st = self._state(feats.device)
+        return torch.ops.surgvid.mstcn_forward_query(feats, offsets, st["id"])
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: [B, f_dim, T] -> [stages, B, out_features, T] (mstcn.py:122-130)."""
@@ -158,5 +197,10 @@ class _MstcnOpOwner:
         self._idx = idx
         self.num_stages, self.num_classes = model.num_stages, model.num_classes
 
-    def _native_forward(self, feats, offsets):
-        return self._model()._native_forward(self._idx, feats, offsets)
+    def _native_forward(self, feats, offsets, want_query=False):
+        return self._model()._native_forward(self._idx, feats, offsets, want_query)
+
+    @property
+    def query_dim(self):
+        m = self._model()
+        return 0 if m is None or m._fc_weight is None else int(m._fc_weight.shape[0])

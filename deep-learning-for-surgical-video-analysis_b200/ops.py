@@ -57,6 +57,39 @@ def _(feats, offsets, handle):
     return feats.new_empty((o.num_stages, o.num_classes, feats.shape[0]), dtype=torch.float32)
 
 
+@torch.library.custom_op("surgvid::mstcn_forward_query", mutates_args=())
+def mstcn_forward_query(feats: torch.Tensor, offsets: torch.Tensor, handle: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """`mstcn_forward` plus query[T_total, q] = tanh(feats @ fc.weight.T) from the same pass over the features
+    (Transformer.original_forward, adapter_transformer.py:348)."""
+    owner = _HANDLES[handle]
+    return owner._native_forward(feats, offsets, True)
+
+
+@mstcn_forward_query.register_fake
+def _(feats, offsets, handle):
+    o = _HANDLES[handle]
+    return (feats.new_empty((o.num_stages, o.num_classes, feats.shape[0]), dtype=torch.float32),
+            feats.new_empty((feats.shape[0], o.query_dim), dtype=torch.float32))
+
+
+def causal_windows(x: torch.Tensor, lengths, len_q: int) -> torch.Tensor:
+    """x [C, T_total] fp32 (row stride may exceed T_total) -> [T_total, len_q, C]: per video, window t holds frames t-len_q+1..t with
+    zeros before the video's first frame (the `inputs` tensor of adapter_transformer.py:335-344)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    C, T = x.shape
+    import numpy as np
+    off = np.zeros(len(lengths) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(np.asarray(list(lengths), dtype=np.int64))
+    if int(off[-1]) != T:
+        raise ValueError("sum(lengths) must equal x.shape[1]")
+    out = torch.empty((T, len_q, C), dtype=torch.float32, device=x.device)
+    rc = _native.lib().sv_op_causal_windows(_ptr(x), x.stride(0), C, off.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), len(lengths), len_q, _ptr(out),
+                                            _stream_ptr(x.device))
+    _native.check(rc, "sv_op_causal_windows")
+    return out
+
+
 def register_handle(owner) -> int:
     hid = id(owner)
     _HANDLES[hid] = owner

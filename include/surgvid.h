@@ -139,6 +139,20 @@ int sv_mstcn_forward(sv_mstcn_handle* h, const float* feats, const int64_t* vide
                      float* logits, void* workspace, size_t workspace_bytes, void* stream);
 int64_t sv_mstcn_last_launch_count(const sv_mstcn_handle* h);
 
+/* Inputs of the Trans-SVNet head (`Transformer.original_forward`, adapter_transformer.py:329-349), i.e. everything
+ * of that function that the reference itself defines (its inner `Transformer2_3_1` module is not part of the reference):
+ *   sv_mstcn_forward_query = sv_mstcn_forward plus, from the SAME pass over the features, the decoder query
+ *       query[T_total, q] = tanh(feats . fc.weight^T)            (adapter_transformer.py:325,348; q = rows of `fc.weight`)
+ *     `fc.weight` ([q <= 16, f_dim], no bias) is handed over with sv_mstcn_set_tensor(h, "fc.weight", ...) before pack_weights;
+ *     query may be NULL (then this is sv_mstcn_forward).
+ *   sv_op_causal_windows: x is [C, T_total] with row stride ldx (e.g. the last stage of `logits`); per video v,
+ *       out[t, j, c] = x[c, t - (len_q - 1) + j], zero where that index precedes the video's first frame
+ *     -> out [T_total, len_q, C] (the `inputs` tensor built by the loop at adapter_transformer.py:335-344). */
+int sv_mstcn_forward_query(sv_mstcn_handle* h, const float* feats, const int64_t* video_offsets, int32_t n_videos, float* logits,
+                           float* query, void* workspace, size_t workspace_bytes, void* stream);
+int sv_op_causal_windows(const float* x, int64_t ldx, int32_t C, const int64_t* video_offsets, int32_t n_videos, int32_t len_q,
+                         float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Single kernels (unit-test surface; the two forwards above are built from exactly these).
  * bf16 tensors are passed as uint16_t*. All pointers are device pointers.
