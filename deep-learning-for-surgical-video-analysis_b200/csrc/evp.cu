@@ -501,6 +501,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   for (int s = 0; s < 4; ++s) {
     if (g[s].H < 1 || g[s].W < 1 || g[s].Hk < 1 || g[s].Wk < 1) return fail(SV_ERR_INVALID, "evp: input too small for the 4-stage pyramid");
   }
+  if (with_flow) {  // MotionGuidedCrossAttention is nn.MultiheadAttention(dim, 8 heads) (mix_transformer_evp.py:866-870)
+    for (int j = 2; j < 4; ++j) {
+      const int hd = c.embed_dims[j] / 8;
+      if (c.embed_dims[j] % 8 != 0 || (hd != 32 && hd != 40 && hd != 64))
+        return fail(SV_ERR_UNSUPPORTED, "evp: flow cross-attention head_dim (C/8) must be 32, 40 or 64 (mit_b0_evp with flow is not supported)");
+    }
+  }
   const int E = c.embedding_dim;
   const int ks[4] = {7, 3, 3, 3}, strd[4] = {4, 2, 2, 2};
 
@@ -812,11 +819,6 @@ int sv_evp_create(const sv_evp_cfg* cfg, sv_evp_handle** out) {
     const int hd = cfg->embed_dims[s] / cfg->num_heads[s];
     if (hd != 32 && hd != 64) return fail(SV_ERR_UNSUPPORTED, "evp: block attention head_dim must be 32 or 64");
   }
-  for (int j = 2; j < 4; ++j) {
-    const int hd = cfg->embed_dims[j] / 8;
-    if (cfg->embed_dims[j] % 8 != 0 || (hd != 32 && hd != 40 && hd != 64))
-      return fail(SV_ERR_UNSUPPORTED, "evp: cross-attention head_dim (C/8) must be 32, 40 or 64");
-  }
   SV_CHECK(cfg->mlp_ratio >= 1 && cfg->embedding_dim % 16 == 0 && cfg->embedding_dim > 0, "evp: mlp_ratio / embedding_dim");
   int dev = 0;
   SV_CUDA_OK(cudaGetDevice(&dev));
@@ -858,7 +860,16 @@ int sv_evp_pack_weights(sv_evp_handle* h) {
 size_t sv_evp_workspace_bytes(const sv_evp_handle* h, int32_t micro_batch, int32_t H, int32_t W) {
   if (!h || micro_batch <= 0 || H <= 0 || W <= 0) return 0;
   size_t bytes = 0;
-  if (sv::build(const_cast<sv_evp*>(h), nullptr, nullptr, micro_batch, H, W, true, &bytes) != SV_OK) return 0;
+  // sized for the larger of the two schedules (with the flow branch); configurations whose flow branch is unsupported
+  // (cross-attention head_dim, see build()) can only ever run without it
+  const bool flow_ok = [&] {
+    for (int j = 2; j < 4; ++j) {
+      const int hd = h->cfg.embed_dims[j] / 8;
+      if (h->cfg.embed_dims[j] % 8 != 0 || (hd != 32 && hd != 40 && hd != 64)) return false;
+    }
+    return true;
+  }();
+  if (sv::build(const_cast<sv_evp*>(h), nullptr, nullptr, micro_batch, H, W, flow_ok, &bytes) != SV_OK) return 0;
   return bytes;
 }
 
