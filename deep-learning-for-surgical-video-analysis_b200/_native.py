@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsurgvid.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "dwconv_tma.cu", "stem.cu", "mstcn.cu", "evp.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "dwconv_tma.cu", "stem.cu", "mixffn.cu", "mstcn.cu", "evp.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 SV_OK = 0
@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "sv_mstcn_create", "sv_mstcn_destroy", "sv_mstcn_set_tensor", "sv_mstcn_pack_weights", "sv_mstcn_workspace_bytes",
     "sv_mstcn_forward", "sv_mstcn_last_launch_count", "sv_mstcn_forward_query", "sv_op_causal_windows",
     "sv_op_gemm_bf16", "sv_op_layernorm", "sv_op_im2col", "sv_op_dwconv3x3_gelu", "sv_op_attention", "sv_op_gauss5x5",
-    "sv_op_bilinear_tokens", "sv_op_token_mean", "sv_op_stem_conv",
+    "sv_op_bilinear_tokens", "sv_op_token_mean", "sv_op_stem_conv", "sv_op_mixffn_fc2",
     "sv_prep_create", "sv_prep_destroy", "sv_prep_workspace_bytes", "sv_prep_images", "sv_prep_flow",
 ]
 
@@ -124,6 +124,8 @@ def _declare(lib):
     lib.sv_op_stem_conv.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p]
     lib.sv_op_token_mean.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
+    lib.sv_op_mixffn_fc2.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_void_p]
     lib.sv_prep_create.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, f32p, f32p, POINTER(c_void_p)]
     lib.sv_prep_destroy.argtypes = [c_void_p]
     lib.sv_prep_workspace_bytes.argtypes = [c_void_p, c_int32]

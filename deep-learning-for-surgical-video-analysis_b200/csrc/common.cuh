@@ -133,6 +133,37 @@ __device__ __forceinline__ void f2_gelu_erf_poly_x2(f32x2& xa, f32x2& xb) {
 #undef SV_C2
 }
 
+// four independent evaluations, Horner steps in lockstep (used where only two warps share a scheduler)
+__device__ __forceinline__ void f2_gelu_erf_poly_x4(f32x2& xa, f32x2& xb, f32x2& xc, f32x2& xd) {
+  const float lim = 4.2426406871192851f;
+  auto clamp2 = [&](f32x2 v) {
+    float v0, v1;
+    f2_unpack(v, v0, v1);
+    return f2_pack(fminf(fmaxf(v0, -lim), lim), fminf(fmaxf(v1, -lim), lim));
+  };
+  const f32x2 ca = clamp2(xa), cb = clamp2(xb), cc = clamp2(xc), cd = clamp2(xd);
+  const f32x2 wa = f2_mul(ca, ca), wb = f2_mul(cb, cb), wc = f2_mul(cc, cc), wd = f2_mul(cd, cd);
+#define SV_C2(v) f2_pack(v, v)
+  f32x2 qa = f2_fma(SV_C2(5.626770213e-11f), wa, SV_C2(-5.371870724e-09f));
+  f32x2 qb = f2_fma(SV_C2(5.626770213e-11f), wb, SV_C2(-5.371870724e-09f));
+  f32x2 qc = f2_fma(SV_C2(5.626770213e-11f), wc, SV_C2(-5.371870724e-09f));
+  f32x2 qd = f2_fma(SV_C2(5.626770213e-11f), wd, SV_C2(-5.371870724e-09f));
+#define SV_STEP(c) qa = f2_fma(qa, wa, SV_C2(c)); qb = f2_fma(qb, wb, SV_C2(c)); qc = f2_fma(qc, wc, SV_C2(c)); qd = f2_fma(qd, wd, SV_C2(c));
+  SV_STEP(2.268296714e-07f)
+  SV_STEP(-5.646215765e-06f)
+  SV_STEP(9.359063167e-05f)
+  SV_STEP(-1.109400333e-03f)
+  SV_STEP(9.818119241e-03f)
+  SV_STEP(-6.634692395e-02f)
+  SV_STEP(3.989031282e-01f)
+#undef SV_STEP
+  xa = f2_fma(f2_mul(xa, ca), qa, f2_mul(xa, SV_C2(0.5f)));
+  xb = f2_fma(f2_mul(xb, cb), qb, f2_mul(xb, SV_C2(0.5f)));
+  xc = f2_fma(f2_mul(xc, cc), qc, f2_mul(xc, SV_C2(0.5f)));
+  xd = f2_fma(f2_mul(xd, cd), qd, f2_mul(xd, SV_C2(0.5f)));
+#undef SV_C2
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "gemm.cuh"
+#include "gemm_epi.cuh"
 #include "ptx.cuh"
 
 namespace sv {
@@ -37,63 +38,9 @@ constexpr int kTmemCols = 512;                    // 2 accumulator buffers x 256
 constexpr int kAccStride = 256;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSmemBudget = 184320;               // operand ring budget (bytes), + 1 KB alignment slack
-constexpr int kStageLd = 36;                      // epilogue staging row stride (floats): 32 columns + 4 pad (conflict-free)
 constexpr int kStagingBytes = kEpiWarps * 32 * kStageLd * 4;  // per epilogue warp: 32 rows x 36 floats
 constexpr int kBiasBytes = kEpiWarps * 256 * 4;   // per epilogue warp: this tile's 256 bias values
 constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
-
-// residual rows for one 32-column chunk: 8 passes x (4 rows x 8 lanes x float4)
-template <bool RESID>
-__device__ __forceinline__ void epi_load_residual(float4 (&res)[8], const GemmParams& p, int row_base, int n, bool col_ok) {
-  if constexpr (RESID) {
-#pragma unroll
-    for (int ps = 0; ps < 8; ++ps) {
-      const int row = row_base + ps * 4;
-      res[ps] = (col_ok && row < p.M) ? *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(row) * p.ldr + n)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
-}
-
-// accumulator registers (thread = row) -> staging tile (transpose point)
-__device__ __forceinline__ void epi_park(float* stg, int lane, const uint32_t (&r)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j)
-    *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
-        make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-}
-
-// staging tile -> bias / activation / residual / cast -> global, 8 lanes per 128-byte row segment
-template <int ACT, bool OUT_F32, bool RESID>
-__device__ __forceinline__ void epi_store(const GemmParams& p, const float* stg, const float* bias_s, const float4 (&res)[8], int row_base,
-                                          int n, int c_local, bool col_ok, int sub_row, int c4) {
-  const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c_local);
-  const long long out_off = static_cast<long long>(row_base) * p.ldc + n;
-  const long long row_step = 4 * p.ldc;
-#pragma unroll
-  for (int ps = 0; ps < 8; ++ps) {
-    const int row = row_base + ps * 4;
-    float4 v = *reinterpret_cast<const float4*>(stg + (ps * 4 + sub_row) * kStageLd + c4);
-    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-    if constexpr (ACT == ACT_GELU) {
-      if constexpr (OUT_F32) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-      else { v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w); }
-    } else if constexpr (ACT == ACT_RELU) {
-      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-    }
-    if constexpr (RESID) { v.x += res[ps].x; v.y += res[ps].y; v.z += res[ps].z; v.w += res[ps].w; }
-    if (col_ok && row < p.M) {
-      if constexpr (OUT_F32) {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + out_off + ps * row_step) = v;
-      } else {
-        uint2 o;
-        o.x = pack_bf16x2(v.x, v.y);
-        o.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + out_off + ps * row_step) = o;
-      }
-    }
-  }
-}
 
 // PAIR = true: the kernel runs as 2-CTA clusters (tcgen05 cta_group::2).  Each CTA stages its own 128 rows of A and HALF of
 // the B tile (block_n/2 rows); the leader CTA (cluster rank 0) issues one M=256 MMA per k-step that reads both CTAs' shared
@@ -266,7 +213,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       }
       float4 res_a[8], res_b[8];
-      epi_load_residual<RESID>(res_a, p, row_base, n0 + half * 32 + c4, half * 32 + c4 < n_valid);
+      epi_load_residual<RESID>(res_a, p.residual, p.ldr, p.M, row_base, n0 + half * 32 + c4, half * 32 + c4 < n_valid);
       __syncwarp();
       ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
       ptx::tc_fence_after();
@@ -280,20 +227,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         epi_park(stg, lane, r_a);
         if (c + 2 < nchunks) {
           ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 2) * 32), r_b);
-          epi_load_residual<RESID>(res_b, p, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid);
+          epi_load_residual<RESID>(res_b, p.residual, p.ldr, p.M, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid);
         }
         __syncwarp();
-        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_a, row_base, n0 + c * 32 + c4, c * 32 + c4, c * 32 + c4 < n_valid, sub_row, c4);
+        epi_store<ACT, OUT_F32, RESID>(p.out, p.ldc, p.M, stg, bias_s, res_a, row_base, n0 + c * 32 + c4, c * 32 + c4, c * 32 + c4 < n_valid, sub_row, c4);
         __syncwarp();
         if (c + 2 >= nchunks) break;
         ptx::tmem_ld_wait();
         epi_park(stg, lane, r_b);
         if (c + 4 < nchunks) {
           ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 4) * 32), r_a);
-          epi_load_residual<RESID>(res_a, p, row_base, n0 + (c + 4) * 32 + c4, (c + 4) * 32 + c4 < n_valid);
+          epi_load_residual<RESID>(res_a, p.residual, p.ldr, p.M, row_base, n0 + (c + 4) * 32 + c4, (c + 4) * 32 + c4 < n_valid);
         }
         __syncwarp();
-        epi_store<ACT, OUT_F32, RESID>(p, stg, bias_s, res_b, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid,
+        epi_store<ACT, OUT_F32, RESID>(p.out, p.ldc, p.M, stg, bias_s, res_b, row_base, n0 + (c + 2) * 32 + c4, (c + 2) * 32 + c4, (c + 2) * 32 + c4 < n_valid,
                                        sub_row, c4);
         __syncwarp();
       }

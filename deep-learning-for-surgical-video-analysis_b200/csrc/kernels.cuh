@@ -38,6 +38,21 @@ bool stem_conv_supported(int Cin, int Cout, int ldw);
 int launch_stem_conv(const float* src, const bf16* w, int ldw, const float* bias, const float* gamma, const float* beta, float eps, int mode,
                      int B, int Cin, int H, int W, int Cout, float* out_f32, bf16* out_bf16, cudaStream_t st);
 
+// DWConv3x3 + GELU fused into the fc2 GEMM as the producer of its A tiles (mixffn.cu):
+//   x[M, N] += bias + GELU(dwconv3x3(h1) + b_dw) @ Wcat[:, :hidden]^T (+ tail[M, tail_cols] @ Wcat[:, hidden:]^T)
+// h1: [frames, H, W, hidden] bf16; w10c: fp32 [10, hidden] = 9 taps (kh*3+kw) then the depthwise bias; x fp32 in place.
+struct MixffnPlan {
+  CUtensorMap tmap_h1, tmap_dw, tmap_w, tmap_t;
+  alignas(8) unsigned char params[128];
+  int grid = 0;
+  size_t smem_bytes = 0;
+  double flops = 0.0;
+};
+bool mixffn_fc2_supported(int H, int W, int hidden, int N, int tail_cols);
+int mixffn_fc2_plan(const bf16* h1, const float* w10c, const bf16* Wcat, int64_t ldw, const float* bias, const bf16* tail, int64_t ldt,
+                    int tail_cols, float* x, int64_t ldx, int frames, int H, int W, int hidden, int N, MixffnPlan* plan);
+int mixffn_fc2_launch(const MixffnPlan& plan, cudaStream_t st);
+
 inline int conv_out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 
 }  // namespace sv

@@ -195,6 +195,22 @@ def token_mean(x: torch.Tensor, tokens: int) -> torch.Tensor:
     return out
 
 
+def mixffn_fc2(h1: torch.Tensor, w9c: torch.Tensor, dw_bias: torch.Tensor, wcat: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor,
+               tail: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [B*H*W, N] fp32 (updated IN PLACE and returned) += bias + GELU(dwconv3x3(h1) + dw_bias) @ wcat[:, :hidden].T (+ tail @ wcat[:, hidden:].T).
+    h1 [B,H,W,hidden] bf16, w9c [9,hidden] fp32, wcat [N, hidden(+tail cols)] bf16, tail [B*H*W, cols] bf16."""
+    _require_cuda(h1, w9c, dw_bias, wcat, bias, x, tail)
+    B, H, W, hidden = h1.shape
+    N = wcat.shape[0]
+    w10c = torch.cat([w9c.reshape(9, hidden), dw_bias.reshape(1, hidden)], 0).contiguous().float()
+    tc = 0 if tail is None else tail.shape[1]
+    assert wcat.shape[1] == hidden + tc and x.shape == (B * H * W, N) and x.dtype == torch.float32
+    rc = _native.lib().sv_op_mixffn_fc2(_ptr(h1), _ptr(w10c), _ptr(wcat), wcat.stride(0), _ptr(bias), _ptr(tail), 0 if tail is None else tail.stride(0),
+                                        tc, _ptr(x), x.stride(0), B, H, W, hidden, N, _stream_ptr(h1.device))
+    _native.check(rc, "sv_op_mixffn_fc2")
+    return x
+
+
 def stem_conv(src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None,
               eps: float = 1e-5, relu: bool = False):
     """src [B,Cin,H,W] fp32; weight [Cout,Cin,7,7] fp32 (packed here to the kernel's (kh,kw,cin) bf16 layout) -> (fp32, bf16) token-major

@@ -202,6 +202,15 @@ int sv_op_stem_conv(const float* src, const uint16_t* w, int32_t ldw, const floa
                     float eps, int32_t relu, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, float* out_f32,
                     uint16_t* out_bf16, void* stream);
 
+/* Second half of the MixFFN in one kernel (Mlp.forward, mix_transformer_evp.py:63-66): the depthwise 3x3 conv + GELU is the producer
+ * of the fc2 GEMM's A tiles, so GELU(DWConv(h1)) never goes to memory.
+ *   x[M, N] (fp32, in place) += bias[N] + GELU(dwconv3x3(h1) + b_dw) . Wcat[:, :hidden]^T  (+ tail[M, tail_cols] . Wcat[:, hidden:]^T)
+ * h1: bf16 [frames, H, W, hidden] (M = frames*H*W); w10c: fp32 [10, hidden] = 9 taps (kh*3+kw) then the depthwise bias;
+ * Wcat: bf16 [N, ldw]; tail: bf16 [M, ldt] or NULL with tail_cols == 0.  W must be even and <= 128; returns SV_ERR_INVALID otherwise. */
+int sv_op_mixffn_fc2(const uint16_t* h1, const float* w10c, const uint16_t* Wcat, int64_t ldw, const float* bias, const uint16_t* tail,
+                     int64_t ldt, int32_t tail_cols, float* x, int64_t ldx, int32_t frames, int32_t H, int32_t W, int32_t hidden, int32_t N,
+                     void* stream);
+
 /* mean over `tokens` consecutive rows of fp32 [B*tokens, C] -> [B, C] (AdaptiveAvgPool2d(1), segformer_head.py:167). */
 int sv_op_token_mean(const float* x, int32_t B, int32_t tokens, int32_t C, float* out, void* stream);
 

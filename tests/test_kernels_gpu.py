@@ -217,3 +217,35 @@ def test_gemm_cta_pair_mode(M, N, K, monkeypatch):
     assert torch.equal(pair, single)
     ref2 = F.gelu(a.float() @ w.float().t() + bias)
     assert (pair_bf16.float() - ref2).abs().max().item() < 3e-2 * max(1.0, ref2.abs().max().item())
+
+
+@pytest.mark.parametrize("cfg", [
+    # (frames, H, W, hidden, N, tail_cols): the three fusable stages of mit_b3_evp at 224^2, a no-tail case, ragged row tiles,
+    # and enough frames that every CTA of the persistent grid walks several tiles
+    (3, 14, 14, 1280, 320, 80), (2, 56, 56, 256, 64, 16), (2, 28, 28, 512, 128, 32), (2, 14, 14, 1280, 320, 0),
+    (2, 11, 12, 128, 64, 0), (1, 9, 14, 64, 32, 8), (200, 14, 14, 1280, 320, 80), (3, 30, 54, 1280, 320, 80)])
+def test_mixffn_fc2_fused(cfg):
+    """x += bias + GELU(dwconv3x3(h1) + b_dw) @ W[:, :hidden].T + tail @ W[:, hidden:].T as one kernel (mixffn.cu) against the same math
+    in fp32 on the bf16-rounded operands (the hidden tensor is rounded to bf16 before the GEMM, exactly as the unfused path stores it)."""
+    B, H, W, hid, N, tc = cfg
+    h1 = _rand((B, H, W, hid), 70, dtype=torch.bfloat16)
+    w = _rand((hid, 1, 3, 3), 71, 0.4)
+    bdw = _rand((hid,), 72, 0.2)
+    wcat = _rand((N, hid + tc), 73, 1.0 / math.sqrt(hid), dtype=torch.bfloat16)
+    bias = _rand((N,), 74, 0.3)
+    tail = _rand((B * H * W, tc), 75, dtype=torch.bfloat16) if tc else None
+    x0 = _rand((B * H * W, N), 76)
+    x = x0.clone()
+    ops.mixffn_fc2(h1, w.view(hid, 9).t().contiguous(), bdw, wcat, bias, x, tail)
+    torch.cuda.synchronize()
+    h2 = F.gelu(F.conv2d(h1.float().permute(0, 3, 1, 2), w, bdw, padding=1, groups=hid)).permute(0, 2, 3, 1).reshape(B * H * W, hid)
+    ref = x0 + bias + h2.bfloat16().float() @ wcat[:, :hid].float().t()
+    if tc:
+        ref = ref + tail.float() @ wcat[:, hid:].float().t()
+    err = (x - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+    # and against the stand-alone kernels (DWConv+GELU kernel -> tcgen05 GEMM with fp32 residual)
+    h2k = ops.dwconv3x3_gelu(h1, w.view(hid, 9).t().contiguous(), bdw).reshape(B * H * W, hid)
+    a = torch.cat([h2k, tail], 1).contiguous() if tc else h2k
+    unf = ops.gemm_bf16(a, wcat, bias, residual=x0, out_dtype=torch.float32)
+    assert (x - unf).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
