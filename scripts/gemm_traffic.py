@@ -1,0 +1,37 @@
+"""Derive per-launch DRAM traffic and per-class duration shares from an ncu launch list
+(`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv`).
+usage: python scripts/gemm_traffic.py <launches.csv> [out.json] [source note]"""
+import collections, csv, json, sys
+
+path = sys.argv[1]
+rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) >= 15 and r[0].isdigit()]
+per = collections.OrderedDict()
+for r in rows:
+    d = per.setdefault(int(r[0]), {"kernel": r[4]})
+    d[r[12]] = float(r[14]) * (1e-3 if r[13] == "ns" and False else 1.0)
+    d.setdefault("units", {})[r[12]] = r[13]
+cls = collections.OrderedDict()
+def klass(name):
+    for k in ("gemm_bf16_tcgen05", "layernorm", "im2col", "dwconv3x3_gelu", "attention", "gauss5x5", "bilinear", "token_mean", "stem_conv", "mstcn", "classify", "prep_"):
+        if k in name: return k
+    return "other"
+tot = 0.0
+for i, d in per.items():
+    k = klass(d["kernel"])
+    c = cls.setdefault(k, {"launches": 0, "time": 0.0, "rd": 0.0, "wr": 0.0})
+    c["launches"] += 1
+    t = d.get("gpu__time_duration.sum", 0.0)
+    if d["units"].get("gpu__time_duration.sum") == "us": t *= 1e3
+    if d["units"].get("gpu__time_duration.sum") == "ms": t *= 1e6
+    c["time"] += t; tot += t
+    c["rd"] += d.get("dram__bytes_read.sum", 0.0); c["wr"] += d.get("dram__bytes_write.sum", 0.0)
+print(f"{len(per)} launches, {tot/1e6:.2f} ms total under ncu (cold-cache, serialised)")
+for k, c in cls.items():
+    print(f"  {k:20s} launches {c['launches']:4d}  time share {c['time']/tot:.3f}  dram rd {c['rd']/1e9:7.2f} GB  wr {c['wr']/1e9:7.2f} GB")
+g = cls.get("gemm_bf16_tcgen05")
+if g and len(sys.argv) > 2:
+    out = {"kernel": "gemm_bf16_tcgen05_kernel", "traffic_bytes_per_launch": int((g["rd"] + g["wr"]) / g["launches"]), "launches": g["launches"],
+           "dram_bytes_read": g["rd"], "dram_bytes_write": g["wr"], "source": sys.argv[3] if len(sys.argv) > 3 else path,
+           "class_time_shares_under_ncu": {k: round(c["time"] / tot, 4) for k, c in cls.items()}}
+    json.dump(out, open(sys.argv[2], "w"), indent=1)
+    print("wrote", sys.argv[2], out["traffic_bytes_per_launch"])
