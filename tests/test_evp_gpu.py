@@ -151,3 +151,27 @@ def test_other_variants_match_oracle(variant, hw, with_flow):
     if variant == "mit_b0_evp":
         with pytest.raises(RuntimeError, match="head_dim"):
             m(x.to(DEV), seg.to(DEV), torch.zeros(3, 2, hw[0], hw[1], device=DEV), return_features=True)
+
+
+def test_full_size_video_properties():
+    """BASELINE configs[1] at full size (one 2 300-frame video, the bench's micro-batch of 800) through size-independent properties:
+    (1) frames are independent, so the features of the whole video are bit-identical to those of any sub-range processed on its own
+        and do not depend on the micro-batch size (800 / 200 / 37);
+    (2) a sample of frames matches the fp32 oracle within the parity tolerance."""
+    m, sd = _model("stress")
+    T = 2300
+    x, seg, flow = S.synth_frames(T, seed=4242, device=DEV)
+    with torch.no_grad():
+        m.micro_batch = 800
+        full = m(x, seg, flow, return_features=True).clone()
+        m.micro_batch = 200
+        part = m(x[1500:2100], seg[1500:2100], flow[1500:2100], return_features=True).clone()
+        m.micro_batch = 37
+        tail = m(x[2200:], seg[2200:], flow[2200:], return_features=True).clone()
+    m.micro_batch = 800
+    assert full.shape == (T, 2048) and bool(torch.isfinite(full).all())
+    assert torch.equal(full[1500:2100], part)
+    assert torch.equal(full[2200:], tail)
+    idx = [0, 799, 800, 1601, 2299]
+    ref = EO.evp_forward(sd, CFG, x[idx].cpu(), seg[idx].cpu(), flow[idx].cpu())
+    _check(full[idx], ref, "2300-frame video, sampled frames vs oracle")

@@ -82,3 +82,28 @@ def test_causality_on_device():
     with torch.no_grad():
         oa, ob = m.forward_videos(a, [900]), m.forward_videos(b, [900])
     assert torch.equal(oa[..., :600], ob[..., :600]) and not torch.equal(oa[..., 600:], ob[..., 600:])
+
+
+def test_full_size_cholec80_batch_properties():
+    """BASELINE configs[3] at full size: the 80 Cholec80-shaped sequences (184 578 frames) in ONE batched call.  Size-independent
+    properties: (1) each video's logits are bit-identical to running that video alone (videos are independent, history never crosses
+    an offset); (2) causality: truncating a video leaves the logits of the kept prefix unchanged."""
+    lengths = S.cholec80_video_lengths()
+    assert len(lengths) == 80 and sum(lengths) == 184578
+    m = MultiStageModel_S(2, 8, 32, 2048, 14, True)
+    m.load_state_dict(S.synth_mstcn_state_dict(2, 8, 32, 2048, 14, seed=7, mode="phase"))
+    m = m.to(DEV).eval()
+    feats = S.synth_lfb_features(sum(lengths), seed=31).to(DEV)
+    with torch.no_grad():
+        allv = m.forward_videos(feats, lengths)
+        assert allv.shape == (2, 14, sum(lengths)) and bool(torch.isfinite(allv).all())
+        offs = [0]
+        for n in lengths:
+            offs.append(offs[-1] + n)
+        for v in (0, 17, 79):
+            one = m.forward_videos(feats[offs[v]:offs[v + 1]], [lengths[v]])
+            assert torch.equal(one, allv[:, :, offs[v]:offs[v + 1]])
+        v = 40
+        cut = lengths[v] // 2
+        pre = m.forward_videos(feats[offs[v]:offs[v] + cut], [cut])
+        assert torch.equal(pre, allv[:, :, offs[v]:offs[v] + cut])
