@@ -45,14 +45,27 @@ class LFBExtractor:
     """End-to-end feature extraction from HOST buffers through the drop-in model (the call a user of the reference
     makes, with the reference's batch size of 200 by default: generate_evp_LFB.py:36 `--val`)."""
 
-    def __init__(self, model, batch_size: int = 200, device: Optional[torch.device] = None):
+    def __init__(self, model, batch_size: int = 200, device: Optional[torch.device] = None, ramp_start: Optional[int] = None):
         self.model = model
         self.batch_size = int(batch_size)
+        # first batch of the ramp-up schedule (see _schedule); default batch_size / 8 (measured best of 25..800 at batch 800, scripts/e2e_ramp.py)
+        self.ramp_start = max(1, int(ramp_start) if ramp_start is not None else self.batch_size // 8)
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self._copy_stream = torch.cuda.Stream(self.device)
         self._dev = None  # double-buffered device staging
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+
+    def _schedule(self, N: int):
+        """Ramp-up schedule: small first batches so the kernels start while the bulk of the input is still crossing PCIe
+        (only the first copy of a call is not overlapped with compute), doubling up to batch_size."""
+        starts, b0, ramp = [], 0, self.ramp_start
+        while b0 < N:
+            n = min(ramp, self.batch_size, N - b0)
+            starts.append((b0, n))
+            b0 += n
+            ramp *= 2
+        return starts
 
     def _staging(self, H, W, with_flow):
         key = (H, W, with_flow)
@@ -81,14 +94,7 @@ class LFBExtractor:
             out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
         compute = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
-        # ramp-up schedule: small first batches so the kernels start while the bulk of the input is still crossing PCIe
-        # (only the first copy of a call is not overlapped with compute)
-        starts, b0, ramp = [], 0, max(1, self.batch_size // 4)
-        while b0 < N:
-            n = min(ramp, self.batch_size, N - b0)
-            starts.append((b0, n))
-            b0 += n
-            ramp *= 2
+        starts = self._schedule(N)
         for bi, (b0, n) in enumerate(starts):
             x, s, f, ev_in, ev_free = bufs[bi % 2]
             with torch.cuda.stream(self._copy_stream):
@@ -136,12 +142,7 @@ class LFBExtractor:
             out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
         compute = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
-        starts, b0, ramp = [], 0, max(1, self.batch_size // 4)
-        while b0 < N:
-            n = min(ramp, self.batch_size, N - b0)
-            starts.append((b0, n))
-            b0 += n
-            ramp *= 2
+        starts = self._schedule(N)
         x, s, f = self._pre_out
         for bi, (b0, n) in enumerate(starts):
             fu, su, fl, ev_in, ev_free = self._raw[bi % 2]
