@@ -9,10 +9,14 @@ namespace {
 
 // ------------------------------------------------------------------------------------------ LayerNorm
 // LPR lanes cooperate on one row (32/LPR rows per warp); each lane holds NV float4 of the row in registers.
-// Two-pass (mean, then centred variance) like ATen's CPU/CUDA LayerNorm; biased variance; eps inside sqrt.
-template <int LPR, int NV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, float eps, int64_t rows, int C,
+// Two-pass (mean, then centred variance) like ATen's LayerNorm; biased variance; eps inside the square root.
+// EXACT: C == 4 * LPR * NV, every lane slot is a real element (no per-slot predicates) — true for every width of the model.
+// The kernel is instruction-issue-bound before it is memory-bound, so the arithmetic is kept lean: 1/C is passed in, rstd is one
+// MUFU.RSQ (2 ulp, far below the bf16 rounding of the outputs), normalisation is one FFMA per element with per-channel a = rstd*gamma,
+// b = beta - mean*a.
+template <int LPR, int NV, bool EXACT>
+__global__ void __launch_bounds__(256, 5) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, float inv_c, int64_t rows, int C,
                                                          float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
                                                          bf16* __restrict__ out_patch, int pH, int pW, int psr) {
   constexpr int RPW = 32 / LPR;
@@ -22,13 +26,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int64_t row = warp_global * RPW + lane / LPR;
   const bool row_ok = row < rows;
   const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (row_ok ? row : 0) * C) + sub;
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = sub + i * LPR;
-    if (row_ok && vi < nvec) {
-      v[i] = *reinterpret_cast<const float4*>(x + row * C + vi * 4);
+    if (EXACT || sub + i * LPR < nvec) {
+      v[i] = xr[i * LPR];
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
       v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -36,19 +40,18 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / static_cast<float>(C);
+  const float mean = s * inv_c;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = sub + i * LPR;
-    if (vi < nvec) {
+    if (EXACT || sub + i * LPR < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
       q += (a * a + b * b) + (c * c + d * d);
     }
   }
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
+  const float rstd = rsqrtf(q * inv_c + eps);
   if (!row_ok) return;
   // optional second bf16 copy in "sr-patch" order: token (b,h,w) -> row (b, h/sr, w/sr), column ((h%sr)*sr + w%sr)*C + c,
   // i.e. the A operand of the spatial-reduction conv (k = stride = sr, no padding) as a plain GEMM.
@@ -66,24 +69,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     if (hq < Hk && wq < Wk)
       patch_off = (static_cast<int64_t>((b * Hk + hq) * Wk + wq) << (2 * lg)) * C + (((h & (psr - 1)) << lg) + (w & (psr - 1))) * C;
   }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma) + sub;
+  const float4* b4 = reinterpret_cast<const float4*>(beta) + sub;
+  float* of = out_f32 ? out_f32 + row * C + sub * 4 : nullptr;
+  bf16* ob = out_bf16 ? out_bf16 + row * C + sub * 4 : nullptr;
+  bf16* op = patch_off >= 0 ? out_patch + patch_off + sub * 4 : nullptr;
+  const float nm = -mean * rstd;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int vi = sub + i * LPR;
-    if (vi < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + vi * 4));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + vi * 4));
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + vi * 4) = y;
-      if (out_bf16 != nullptr || patch_off >= 0) {
+    if (EXACT || sub + i * LPR < nvec) {
+      const float4 g = __ldg(g4 + i * LPR);
+      const float4 b = __ldg(b4 + i * LPR);
+      float4 y;   // (v - mean) * rstd * g + b  ==  v * (rstd*g) + (b - mean*rstd*g)
+      y.x = fmaf(v[i].x, rstd * g.x, fmaf(nm, g.x, b.x));
+      y.y = fmaf(v[i].y, rstd * g.y, fmaf(nm, g.y, b.y));
+      y.z = fmaf(v[i].z, rstd * g.z, fmaf(nm, g.z, b.z));
+      y.w = fmaf(v[i].w, rstd * g.w, fmaf(nm, g.w, b.w));
+      if (of) *reinterpret_cast<float4*>(of + i * LPR * 4) = y;
+      if (ob || op) {
         uint2 o;
         o.x = pack_bf16x2(y.x, y.y);
         o.y = pack_bf16x2(y.z, y.w);
-        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + row * C + vi * 4) = o;
-        if (patch_off >= 0) *reinterpret_cast<uint2*>(out_patch + patch_off + vi * 4) = o;
+        if (ob) *reinterpret_cast<uint2*>(ob + i * LPR * 4) = o;
+        if (op) *reinterpret_cast<uint2*>(op + i * LPR * 4) = o;
       }
     }
   }
@@ -95,7 +103,11 @@ int ln_launch(const float* x, const float* g, const float* b, float eps, int64_t
   constexpr int RPW = 32 / LPR;
   const int64_t warps = ceil_div64(rows, RPW);
   const int64_t blocks = ceil_div64(warps, 8);
-  layernorm_kernel<LPR, NV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, rows, C, of, ob, op, pH, pW, psr);
+  const float inv_c = 1.0f / static_cast<float>(C);
+  if (C == 4 * LPR * NV)
+    layernorm_kernel<LPR, NV, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, inv_c, rows, C, of, ob, op, pH, pW, psr);
+  else
+    layernorm_kernel<LPR, NV, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(x, g, b, eps, inv_c, rows, C, of, ob, op, pH, pW, psr);
   return launch_status("layernorm_kernel");
 }
 
@@ -360,6 +372,18 @@ int launch_layernorm_patch(const float* x, const float* gamma, const float* beta
              "layernorm patch geometry (sr must be a power of two)");
   const int nvec = C / 4;
 #define SV_LN(L, N) return ln_launch<L, N>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, out_patch, pH, pW, psr, st)
+  // exact lane mappings first (every slot a real element): the model's widths 16/32/64/128/256/512 and 40/80/160/320
+  if (nvec == 4) SV_LN(4, 1);
+  if (nvec == 8) SV_LN(8, 1);
+  if (nvec == 16) SV_LN(16, 1);
+  if (nvec == 32) SV_LN(16, 2);
+  if (nvec == 64) SV_LN(16, 4);
+  if (nvec == 128) SV_LN(32, 4);
+  if (nvec == 10) SV_LN(2, 5);
+  if (nvec == 20) SV_LN(4, 5);
+  if (nvec == 40) SV_LN(8, 5);
+  if (nvec == 80) SV_LN(16, 5);
+  // anything else: predicated slots
   if (nvec <= 4) SV_LN(4, 1);
   if (nvec <= 8) SV_LN(8, 1);
   if (nvec <= 16) SV_LN(16, 1);
