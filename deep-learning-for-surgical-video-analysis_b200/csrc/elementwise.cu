@@ -113,26 +113,25 @@ int ln_launch(const float* x, const float* g, const float* b, float eps, int64_t
 
 // ------------------------------------------------------------------------------------------ im2col
 // NHWC bf16 source, Cin % 8 == 0: one thread moves one 16-byte channel chunk of one (m, kh, kw) tap.
-__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ src, int B, int Cin, int H, int W, int k, int stride,
-                                                          int pad, int Ho, int Wo, bf16* __restrict__ out, int64_t ldo) {
-  const int cv = Cin >> 3;
-  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * k * k * cv;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = static_cast<int>(idx % cv);
-  int64_t t = idx / cv;
-  const int kw = static_cast<int>(t % k); t /= k;
-  const int kh = static_cast<int>(t % k); t /= k;
-  const int64_t m = t;
-  const int ow = static_cast<int>(m % Wo);
-  const int oh = static_cast<int>((m / Wo) % Ho);
-  const int b = static_cast<int>(m / (static_cast<int64_t>(Wo) * Ho));
-  const int ih = oh * stride - pad + kh;
-  const int iw = ow * stride - pad + kw;
+// grid = (chunks of one output row, Ho, B): the only index arithmetic left per thread is two 32-bit divisions by k*k*cv and cv
+// (the flat 64-bit version spent ~450 instructions per 16 bytes moved and was issue-bound).
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const bf16* __restrict__ src, int Cin, int H, int W, int k, int stride, int pad,
+                                                          int Ho, int Wo, bf16* __restrict__ out, int64_t ldo) {
+  const uint32_t cv = static_cast<uint32_t>(Cin) >> 3;
+  const uint32_t kc = static_cast<uint32_t>(k * k) * cv;            // 16-byte chunks per output pixel
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= static_cast<uint32_t>(Wo) * kc) return;
+  const uint32_t ow = t / kc, j = t - ow * kc;
+  const uint32_t tap = j / cv, c8 = j - tap * cv;
+  const uint32_t kh = tap / static_cast<uint32_t>(k), kw = tap - kh * static_cast<uint32_t>(k);
+  const int oh = blockIdx.y, b = blockIdx.z;
+  const int ih = oh * stride - pad + static_cast<int>(kh);
+  const int iw = static_cast<int>(ow) * stride - pad + static_cast<int>(kw);
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if (ih >= 0 && ih < H && iw >= 0 && iw < W)
     v = __ldg(reinterpret_cast<const uint4*>(src + ((static_cast<int64_t>(b) * H + ih) * W + iw) * Cin + c8 * 8));
-  *reinterpret_cast<uint4*>(out + m * ldo + (kh * k + kw) * Cin + c8 * 8) = v;
+  const int64_t m = (static_cast<int64_t>(b) * Ho + oh) * Wo + ow;
+  *reinterpret_cast<uint4*>(out + m * ldo + j * 8) = v;   // column (kh*k + kw)*Cin + c8*8 == j*8
 }
 
 // NCHW fp32 source (network inputs: Cin = 3 or 2): one thread gathers 8 consecutive k indices (kh,kw,c order).
@@ -266,17 +265,17 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
 // ------------------------------------------------------------------------------------------ Gaussian 5x5 (reflect pad 2)
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-// one thread = 4 horizontally adjacent outputs: 5 rows x 8 taps loaded once (10 loads per output instead of 25)
-__global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int planes, int H, int W) {
-  const int wq = (W + 3) >> 2;
-  const int64_t total = static_cast<int64_t>(planes) * H * wq;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int w0 = static_cast<int>(idx % wq) * 4;
-  const int h = static_cast<int>((idx / wq) % H);
-  const int64_t pl = idx / (static_cast<int64_t>(wq) * H);
+// one thread = 4 horizontally adjacent outputs of one row; block (32, 8), grid (column groups, row groups, planes) — no index
+// divisions.  Interior threads read each of the 5 source rows as three aligned float4 (columns w0-4 .. w0+7) and write one
+// float4; threads touching the left/right border take the scalar reflect path.
+__global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int vec) {
+  const int w0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int h = blockIdx.y * 8 + threadIdx.y;
+  if (w0 >= W || h >= H) return;
+  const int64_t pl = blockIdx.z;
   const float* src = x + pl * H * W;
   const float k1[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};  // outer(k1,k1) == [1 4 6 4 1]^2 / 256 exactly
+  const bool fast = vec && w0 >= 4 && w0 + 8 <= W;   // vec: W % 4 == 0 and 16-byte aligned planes
   int cols[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) cols[j] = reflect_idx(min(w0 + j - 2, W + 1), W);
@@ -285,8 +284,15 @@ __global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__
   for (int dy = 0; dy < 5; ++dy) {
     const float* rowp = src + static_cast<int64_t>(reflect_idx(h + dy - 2, H)) * W;
     float v[8];
+    if (fast) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(rowp + w0 - 4));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(rowp + w0));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(rowp + w0 + 4));
+      v[0] = a.z; v[1] = a.w; v[2] = b.x; v[3] = b.y; v[4] = b.z; v[5] = b.w; v[6] = c.x; v[7] = c.y;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(rowp + cols[j]);
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(rowp + cols[j]);
+    }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       float r = 0.f;
@@ -295,9 +301,14 @@ __global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__
       acc[o] = fmaf(r, k1[dy], acc[o]);
     }
   }
+  float* dst = out + (pl * H + h) * W + w0;
+  if (vec) {
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
 #pragma unroll
-  for (int o = 0; o < 4; ++o)
-    if (w0 + o < W) out[(pl * H + h) * W + w0 + o] = acc[o];
+    for (int o = 0; o < 4; ++o)
+      if (w0 + o < W) dst[o] = acc[o];
+  }
 }
 
 // ------------------------------------------------------------------------------------------ bilinear resize (align_corners=False)
@@ -413,8 +424,10 @@ int launch_im2col(const float* src_nchw_f32, const bf16* src_nhwc_bf16, int B, i
   }
   SV_CHECK(src_nhwc_bf16 != nullptr, "im2col needs a source");
   SV_CHECK(Cin % 8 == 0 && ldo == K, "im2col NHWC path needs Cin%8==0 and ldo==k*k*Cin");
-  const int64_t total = static_cast<int64_t>(B) * Ho * Wo * k * k * (Cin / 8);
-  im2col_nhwc_kernel<<<blocks_for(total), 256, 0, st>>>(src_nhwc_bf16, B, Cin, H, W, k, stride, pad, Ho, Wo, out, ldo);
+  SV_CHECK(Ho <= 65535 && B <= 65535, "im2col grid limits");
+  const int64_t row_chunks = static_cast<int64_t>(Wo) * k * k * (Cin / 8);
+  dim3 grid(static_cast<unsigned>(ceil_div64(row_chunks, 256)), static_cast<unsigned>(Ho), static_cast<unsigned>(B));
+  im2col_nhwc_kernel<<<grid, 256, 0, st>>>(src_nhwc_bf16, Cin, H, W, k, stride, pad, Ho, Wo, out, ldo);
   return launch_status("im2col_nhwc_kernel");
 }
 
@@ -437,7 +450,10 @@ int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, in
 
 int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st) {
   SV_CHECK(H >= 3 && W >= 3, "gauss5x5 needs H,W >= 3 (reflect pad 2)");
-  gauss5x5_kernel<<<blocks_for(static_cast<int64_t>(planes) * H * ((W + 3) / 4)), 256, 0, st>>>(x, out, planes, H, W);
+  SV_CHECK(planes >= 1 && planes <= 65535 && ceil_div(H, 8) <= 65535, "gauss5x5 grid limits");
+  const int vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  dim3 grid(static_cast<unsigned>(ceil_div(ceil_div(W, 4), 32)), static_cast<unsigned>(ceil_div(H, 8)), static_cast<unsigned>(planes));
+  gauss5x5_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, H, W, vec);
   return launch_status("gauss5x5_kernel");
 }
 
