@@ -48,7 +48,7 @@ struct BlockW {
 struct StageW {
   Lin pe, emb, shared, hc;
   Norm pe_norm, hc_norm, norm;
-  std::vector<Lin> lw;
+  Lin lw_all;  // all lightweight_mlp{s}_{i} of the stage stacked along N: T_all = GELU(P . lw_all^T) in ONE GEMM (P does not depend on the block)
   std::vector<BlockW> blk;
 };
 struct CrossW {
@@ -253,10 +253,8 @@ int pack_all(sv_evp* h) {
     S.hc_norm = P.norm("prompt_generator.handcrafted_generator" + sn + ".norm", Cp);
     S.emb = P.linear("prompt_generator.embedding_generator" + sn, Cp, C);
     S.shared = P.linear("prompt_generator.shared_mlp" + sn, C, Cp);
-    S.lw.clear();
     S.blk.clear();
     for (int i = 0; i < c.depths[s]; ++i) {
-      S.lw.push_back(P.linear("prompt_generator.lightweight_mlp" + sn + "_" + std::to_string(i) + ".0", Cp, Cp));
       const std::string bp = "block" + sn + "." + std::to_string(i);
       BlockW B;
       B.n1 = P.norm(bp + ".norm1", C);
@@ -277,6 +275,19 @@ int pack_all(sv_evp* h) {
           for (int t = 0; t < 9; ++t) P.wf[B.dw_w + static_cast<size_t>(t) * hid + ch] = dw->data[static_cast<size_t>(ch) * 9 + t];
       B.dw_b = P.vec(bp + ".mlp.dwconv.dwconv.bias", hid);
       S.blk.push_back(B);
+    }
+    {  // stacked lightweight MLPs: rows [i*Cp, (i+1)*Cp) = lightweight_mlp{s}_{i}.0
+      std::vector<float> wa(static_cast<size_t>(c.depths[s]) * Cp * Cp, 0.f), ba(static_cast<size_t>(c.depths[s]) * Cp, 0.f);
+      bool ok = true;
+      for (int i = 0; i < c.depths[s]; ++i) {
+        const std::string ln = "prompt_generator.lightweight_mlp" + sn + "_" + std::to_string(i) + ".0";
+        const HostTensor* w = P.get(ln + ".weight", {Cp, Cp});
+        const HostTensor* bb = P.get(ln + ".bias", {Cp});
+        if (!w || !bb) { ok = false; break; }
+        std::copy(w->data.begin(), w->data.end(), wa.begin() + static_cast<size_t>(i) * Cp * Cp);
+        std::copy(bb->data.begin(), bb->data.end(), ba.begin() + static_cast<size_t>(i) * Cp);
+      }
+      if (ok) S.lw_all = P.linear_raw(wa.data(), ba.data(), c.depths[s] * Cp, Cp);
     }
     // Adapter fusion: the adapter term of block i+1, shared_mlp(GELU(lightweight_mlp_{i+1}(P))), does not depend on x, so it
     // is added by block i's fc2 GEMM: K-concatenated weight [W_fc2_i | W_shared], bias b_fc2_i + b_shared.
@@ -424,10 +435,13 @@ struct Builder {
     plan->bytes_by_kind[op.kind] += op.alg_bytes;
   }
 
-  void gemm(const bf16* A, int64_t lda, const Lin& l, int M, int act, const float* resid, int64_t ldr, void* out, int64_t ldc, int out_fp32) {
+  // A2/lda2/K2: optional second A segment for the last K2 columns of K (see GemmDesc)
+  void gemm(const bf16* A, int64_t lda, const Lin& l, int M, int act, const float* resid, int64_t ldr, void* out, int64_t ldc, int out_fp32,
+            const bf16* A2 = nullptr, int64_t lda2 = 0, int K2 = 0) {
     if (dry() || status != SV_OK) return;
     GemmDesc d;
     d.A = A; d.lda = lda; d.W = W(l); d.ldw = l.ldw; d.M = M; d.N = l.N; d.bias = Bf(l); d.act = act;
+    d.A2 = A2; d.lda2 = lda2; d.K2 = K2;
     d.K = l.ldw;  // K padded to a multiple of 8; pad columns are zero in both the packed weight and the im2col buffer
     d.residual = resid; d.ldr = ldr; d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
     Op op;
@@ -512,13 +526,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   const int ks[4] = {7, 3, 3, 3}, strd[4] = {4, 2, 2, 2};
 
   // ---- sizes of stage-scoped buffers (max over stages)
-  size_t max_tok_c = 0, max_tok_cp = 0, max_tok_hid = 0, max_tok_hidcat = 0, max_kv_c = 0, max_sr_k = 0, max_col = 0, max_conv_out = 0;
+  size_t max_tok_c = 0, max_tok_cp = 0, max_tok_hid = 0, max_tok_tall = 0, max_kv_c = 0, max_sr_k = 0, max_col = 0, max_conv_out = 0;
   for (int s = 0; s < 4; ++s) {
     const size_t M = static_cast<size_t>(n) * g[s].N, Mk = static_cast<size_t>(n) * g[s].Nkv;
     max_tok_c = std::max(max_tok_c, M * g[s].C);
     max_tok_cp = std::max(max_tok_cp, M * g[s].Cp);
     max_tok_hid = std::max(max_tok_hid, M * g[s].hidden);
-    max_tok_hidcat = std::max(max_tok_hidcat, M * (g[s].hidden + g[s].Cp));
+    max_tok_tall = std::max(max_tok_tall, M * static_cast<size_t>(c.depths[s]) * g[s].Cp);
     max_kv_c = std::max(max_kv_c, Mk * g[s].C);
     if (g[s].sr > 1) max_sr_k = std::max(max_sr_k, Mk * static_cast<size_t>(g[s].sr * g[s].sr * g[s].C));
     const int cin = s == 0 ? 3 : c.embed_dims[s - 1];
@@ -551,13 +565,13 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   bf16* qb = A.get<bf16>(max_tok_c);
   bf16* ob = A.get<bf16>(max_tok_c);
   bf16* Pb = A.get<bf16>(max_tok_cp);
-  bf16* Tb = A.get<bf16>(max_tok_cp);
   bf16* a_sr = A.get<bf16>(std::max<size_t>(max_sr_k, 8));
   float* sr_out = A.get<float>(max_kv_c);
   bf16* srn = A.get<bf16>(max_kv_c);
   bf16* kvb = A.get<bf16>(2 * max_kv_c);
   bf16* h1 = A.get<bf16>(max_tok_hid);
-  bf16* h2 = A.get<bf16>(max_tok_hidcat);  // [M, 4C + C/4]: GELU(dwconv(h1)) | adapter T of the NEXT block
+  bf16* h2 = A.get<bf16>(max_tok_hid);     // [M, 4C]: GELU(dwconv(h1))
+  bf16* T_all = A.get<bf16>(max_tok_tall);  // [M, depth * C/4]: GELU(lightweight_mlp_i(P)) for every block i of the stage
 
   // ---- 0. handcrafted prompts: gaussian(seg) -> 4 chained OverlapPatchEmbeds (mix_transformer_evp.py:718-747)
   b.gauss(seg_g, n * 3, H, W);
@@ -596,16 +610,16 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
       }
       // init_prompt (:749-756): P = handcrafted_s + embedding_generator_s(x)   (constant over depth)
       b.gemm(xn, C, S.emb, M, ACT_NONE, hc_f32[s], G.Cp, Pb, G.Cp, 0);
-      const int ldh = G.hidden + G.Cp;
+      const int ldh = G.hidden;
+      const int ldt = c.depths[s] * G.Cp;
+      // every block's T_i = GELU(lightweight_mlp_i(P)) in one GEMM (P is constant over the depth of the stage)
+      b.gemm(Pb, G.Cp, S.lw_all, M, ACT_GELU, nullptr, 0, T_all, ldt, 0);
       for (int i = 0; i < c.depths[s]; ++i) {
         const BlockW& Bk = S.blk[i];
         const bool has_next = i + 1 < c.depths[s];
-        // get_prompt (:776-815): x += shared_mlp(GELU(lightweight_mlp_i(P))).  Only block 0 does this as its own GEMM pair;
-        // for i >= 1 the term was already added by block i-1's K-concatenated fc2 GEMM (see pack_all).
-        if (i == 0) {
-          b.gemm(Pb, G.Cp, S.lw[0], M, ACT_GELU, nullptr, 0, Tb, G.Cp, 0);
-          b.gemm(Tb, G.Cp, S.shared, M, ACT_NONE, x, C, x, C, 1);
-        }
+        // get_prompt (:776-815): x += shared_mlp(T_i).  Only block 0 does this as its own GEMM; for i >= 1 the term was already
+        // added by block i-1's K-concatenated fc2 GEMM (see pack_all).
+        if (i == 0) b.gemm(T_all, ldt, S.shared, M, ACT_NONE, x, C, x, C, 1);
         // attention (:110-131); LN1 also emits the sr-conv's A operand (non-overlapping sr x sr patches) directly
         if (G.sr > 1) {
           b.ln(x, Bk.n1, 1e-6f, M, nullptr, xn, a_sr, G.H, G.W, G.sr);
@@ -625,8 +639,8 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
         b.gemm(xn, C, Bk.fc1, M, ACT_NONE, nullptr, 0, h1, G.hidden, 0);
         b.dwconv(h1, Bk.dw_w, Bk.dw_b, n, G.H, G.W, G.hidden, h2, ldh);
         if (has_next) {
-          b.gemm(Pb, G.Cp, S.lw[i + 1], M, ACT_GELU, nullptr, 0, h2 + G.hidden, ldh, 0);   // T_{i+1} into the K tail of h2
-          b.gemm(h2, ldh, Bk.fc2cat, M, ACT_NONE, x, C, x, C, 1);                           // x += fc2(h) + shared_mlp(T_{i+1})
+          // x += fc2(h) + shared_mlp(T_{i+1}): A = [h2 | T_{i+1}] as two K segments, W = [W_fc2 | W_shared]
+          b.gemm(h2, ldh, Bk.fc2cat, M, ACT_NONE, x, C, x, C, 1, T_all + static_cast<size_t>(i + 1) * G.Cp, ldt, G.Cp);
         } else {
           b.gemm(h2, ldh, Bk.fc2, M, ACT_NONE, x, C, x, C, 1);
         }

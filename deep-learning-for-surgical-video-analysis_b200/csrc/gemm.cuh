@@ -11,6 +11,11 @@ struct GemmDesc {
   const bf16* W = nullptr;   // [N, K] row-major (nn.Linear weight layout), row stride ldw
   int64_t ldw = 0;
   int M = 0, N = 0, K = 0;
+  // optional second A segment: the last K2 columns of the K dimension are read from A2[:, 0:K2] (row stride lda2) instead of
+  // A[:, K-K2:K]; K - K2 must be a multiple of 64.  Lets a GEMM consume [A | A2] without materialising the concatenation.
+  const bf16* A2 = nullptr;
+  int64_t lda2 = 0;
+  int K2 = 0;
   const float* bias = nullptr;      // [N] or null
   int act = ACT_NONE;
   const float* residual = nullptr;  // [M, N] fp32, row stride ldr, or null (may alias out if out_fp32)
@@ -29,6 +34,7 @@ struct GemmParams {
   int num_tiles;
   int pair;         // 1: 2-CTA clusters; num_tiles counts 256-row pair tiles
   int prefetch;     // k-blocks of the A operand requested into L2 ahead of the shared-memory ring (0 = off)
+  int kb_split;     // k-blocks served by the first A segment (all of them without a second segment)
   int act;
   int out_fp32;
   const float* bias;
@@ -40,6 +46,7 @@ struct GemmParams {
 
 struct GemmPlan {
   CUtensorMap tmap_a;
+  CUtensorMap tmap_a2;   // second A segment (copy of tmap_a when unused)
   CUtensorMap tmap_w;
   GemmParams p;
   int grid = 0;

@@ -48,7 +48,8 @@ constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
 // what bounds the K >= 256 GEMMs of stages 3/4 (operands come from L2, not HBM).
 template <int ACT, bool OUT_F32, bool RESID, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                         const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -71,6 +72,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_a2);
     ptx::prefetch_tensormap(&tmap_w);
   }
   if (warp == 1) {
@@ -126,14 +128,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
+          const bool seg2 = kb >= p.kb_split;   // second A segment (e.g. the adapter tensor next to the MixFFN hidden)
+          const CUtensorMap* ma = seg2 ? &tmap_a2 : &tmap_a;
+          const int ka = (seg2 ? kb - p.kb_split : kb) * kBlockK;
           if (PAIR) {
             // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
             if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
-            ptx::tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+            ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], ka, m0);
             ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            ptx::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * kBlockK, m0);
+            ptx::tma_load_2d(sa, ma, &full_bar[stage], ka, m0);
             ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
           }
           if (++stage == S) { stage = 0; phase ^= 1u; }
@@ -337,7 +342,9 @@ int gemm_pick_block_n(int M, int N, int K, int num_sms) {
 int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   SV_CHECK(d.M > 0 && d.N > 0 && d.K > 0, "GEMM dims must be positive");
   SV_CHECK(d.K % 8 == 0 && d.N % 8 == 0, "GEMM needs K%8==0 and N%8==0");
-  SV_CHECK(d.lda >= d.K && d.ldw >= d.K && d.ldc >= d.N, "GEMM leading dimensions too small");
+  SV_CHECK(d.K2 >= 0 && d.K2 < d.K && (d.K2 == 0 || (d.A2 != nullptr && (d.K - d.K2) % kBlockK == 0 && d.K2 % 8 == 0 && d.lda2 >= d.K2)),
+           "GEMM second A segment: K-K2 must be a multiple of 64, K2 % 8 == 0");
+  SV_CHECK(d.lda >= d.K - d.K2 && d.ldw >= d.K && d.ldc >= d.N, "GEMM leading dimensions too small");
   SV_CHECK(d.A && d.W && d.out, "GEMM null operand");
   SV_CHECK((reinterpret_cast<uintptr_t>(d.out) & 15) == 0 && d.ldc % (d.out_fp32 ? 4 : 8) == 0, "GEMM output must be 16B-aligned rows");
   if (d.residual) SV_CHECK((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && d.ldr % 4 == 0 && d.ldr >= d.N, "GEMM residual alignment");
@@ -368,14 +375,17 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   plan->grid = p.pair ? 2 * std::min(p.num_tiles, sms / 2) : std::min(p.num_tiles, sms);
   plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes_eff + kEpiSmemBytes + 1024;
   plan->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
-  SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K, d.lda, kBlockM));
+  p.kb_split = ceil_div(d.K - d.K2, kBlockK);
+  SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K - d.K2, d.lda, kBlockM));
+  if (d.K2 > 0) SV_TRY(encode_operand_map(&plan->tmap_a2, d.A2, d.M, d.K2, d.lda2, kBlockM));
+  else plan->tmap_a2 = plan->tmap_a;
   SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, b_rows));
   return SV_OK;
 }
 
 namespace {
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const GemmParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
 
 template <int ACT, bool PAIR>
 GemmKernelFn pick_kernel(int out_fp32, bool resid) {
@@ -426,11 +436,11 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_w, plan.p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.p);
     if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaLaunchKernelEx(gemm pair): ") + cudaGetErrorString(e));
     return SV_OK;
   }
-  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_w, plan.p);
+  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.p);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
@@ -445,6 +455,20 @@ extern "C" int sv_op_gemm_bf16(const uint16_t* A, int64_t lda, const uint16_t* W
   d.M = M; d.N = N; d.K = K; d.bias = bias; d.act = act; d.residual = residual; d.ldr = ldr;
   d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
   if (const char* e = getenv("SURGVID_GEMM_PAIR")) d.pair = atoi(e);  // test hook: force CTA-pair mode on (1) / off (0)
+  sv::GemmPlan plan;
+  SV_TRY(sv::gemm_plan(d, &plan));
+  return sv::gemm_launch(plan, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sv_op_gemm_bf16_cat(const uint16_t* A, int64_t lda, const uint16_t* A2, int64_t lda2, int32_t K2, const uint16_t* W, int64_t ldw,
+                                   int32_t M, int32_t N, int32_t K, const float* bias, int32_t act, const float* residual, int64_t ldr, void* out,
+                                   int64_t ldc, int32_t out_fp32, void* stream) {
+  sv::GemmDesc d;
+  d.A = reinterpret_cast<const sv::bf16*>(A); d.lda = lda;
+  d.A2 = reinterpret_cast<const sv::bf16*>(A2); d.lda2 = lda2; d.K2 = K2;
+  d.W = reinterpret_cast<const sv::bf16*>(W); d.ldw = ldw;
+  d.M = M; d.N = N; d.K = K; d.bias = bias; d.act = act; d.residual = residual; d.ldr = ldr;
+  d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
   sv::GemmPlan plan;
   SV_TRY(sv::gemm_plan(d, &plan));
   return sv::gemm_launch(plan, static_cast<cudaStream_t>(stream));

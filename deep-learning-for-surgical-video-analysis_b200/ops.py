@@ -119,6 +119,24 @@ def gemm_bf16(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     return out
 
 
+def gemm_bf16_cat(a: torch.Tensor, a2: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0,
+                  residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = act(cat([a, a2], 1) @ w.T + bias) (+ residual) without building the concatenation; a [M,K1] (K1 % 64 == 0), a2 [M,K2] bf16
+    (row strides may exceed the widths), w [N, K1+K2] bf16."""
+    _require_cuda(a, a2, w, bias, residual, out)
+    M, K1 = a.shape
+    K2 = a2.shape[1]
+    N = w.shape[0]
+    assert w.shape[1] == K1 + K2 and a2.shape[0] == M and a.stride(1) == 1 and a2.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    rc = _native.lib().sv_op_gemm_bf16_cat(_ptr(a), a.stride(0), _ptr(a2), a2.stride(0), K2, _ptr(w), w.stride(0), M, N, K1 + K2, _ptr(bias), act,
+                                           _ptr(residual), 0 if residual is None else residual.stride(0), _ptr(out), out.stride(0),
+                                           int(out.dtype == torch.float32), _stream_ptr(a.device))
+    _native.check(rc, "sv_op_gemm_bf16_cat")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, want_f32=False, want_bf16=True):
     _require_cuda(x, gamma, beta)
     rows, C = x.shape

@@ -202,6 +202,14 @@ int sv_op_stem_conv(const float* src, const uint16_t* w, int32_t ldw, const floa
                     float eps, int32_t relu, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, float* out_f32,
                     uint16_t* out_bf16, void* stream);
 
+/* sv_op_gemm_bf16 with the A operand given as two K segments: out = act([A | A2] . W^T + bias) (+ residual), where the last K2 of
+ * the K columns come from A2[:, 0:K2] (row stride lda2) and the first K - K2 (a multiple of 64) from A.  This is how block i's fc2
+ * consumes [GELU(DWConv(h)) | T_{i+1}] against [W_fc2 | W_shared] (Mlp.forward + PromptGenerator.get_prompt,
+ * mix_transformer_evp.py:60-67, 776-815) without materialising the concatenation. */
+int sv_op_gemm_bf16_cat(const uint16_t* A, int64_t lda, const uint16_t* A2, int64_t lda2, int32_t K2, const uint16_t* W, int64_t ldw,
+                        int32_t M, int32_t N, int32_t K, const float* bias, int32_t act, const float* residual, int64_t ldr, void* out,
+                        int64_t ldc, int32_t out_fp32, void* stream);
+
 /* Second half of the MixFFN in one kernel (Mlp.forward, mix_transformer_evp.py:63-66): the depthwise 3x3 conv + GELU is the producer
  * of the fc2 GEMM's A tiles, so GELU(DWConv(h1)) never goes to memory.
  *   x[M, N] (fp32, in place) += bias[N] + GELU(dwconv3x3(h1) + b_dw) . Wcat[:, :hidden]^T  (+ tail[M, tail_cols] . Wcat[:, hidden:]^T)

@@ -249,3 +249,21 @@ def test_mixffn_fc2_fused(cfg):
     a = torch.cat([h2k, tail], 1).contiguous() if tc else h2k
     unf = ops.gemm_bf16(a, wcat, bias, residual=x0, out_dtype=torch.float32)
     assert (x - unf).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K1,K2,strided", [(300, 64, 256, 16, False), (1000, 320, 1280, 80, True), (129, 128, 512, 32, True), (5000, 320, 64, 8, False)])
+def test_gemm_two_segment_a_operand(M, N, K1, K2, strided):
+    """[A | A2] @ W^T with the two K segments read from different buffers == the GEMM on the materialised concatenation (bit-identical:
+    same tiles, same accumulation order), in the residual fp32 form the model uses for fc2 + adapter."""
+    a = _rand((M, K1), 80, dtype=torch.bfloat16)
+    big = _rand((M, 3 * K2 + 8), 81, dtype=torch.bfloat16)       # a2 is a column slice of a wider tensor (row stride > K2), like T_all
+    a2 = big[:, K2:2 * K2] if strided else big[:, :K2].contiguous()
+    w = _rand((N, K1 + K2), 82, 1.0 / math.sqrt(K1 + K2), dtype=torch.bfloat16)
+    bias = _rand((N,), 83, 0.2)
+    x0 = _rand((M, N), 84)
+    got = ops.gemm_bf16_cat(a, a2, w, bias, residual=x0, out_dtype=torch.float32)
+    want = ops.gemm_bf16(torch.cat([a, a2], 1).contiguous(), w, bias, residual=x0, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    ref = x0 + bias + torch.cat([a, a2], 1).float() @ w.float().t()
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
