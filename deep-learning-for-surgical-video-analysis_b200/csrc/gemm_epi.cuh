@@ -43,8 +43,16 @@ __device__ __forceinline__ void epi_store(void* out, long long ldc, int row_limi
     float4 v = *reinterpret_cast<const float4*>(stg + (ps * 4 + sub_row) * kStageLd + c4);
     v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
     if constexpr (ACT == ACT_GELU) {
-      if constexpr (OUT_F32) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
-      else { v.x = gelu_erf_fast(v.x); v.y = gelu_erf_fast(v.y); v.z = gelu_erf_fast(v.z); v.w = gelu_erf_fast(v.w); }
+      if constexpr (OUT_F32) {
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+      } else {
+        // bf16 result: the packed degree-8 erf polynomial (|error| <= 6e-5, below the bf16 rounding) — two FFMA2 chains instead of
+        // four scalar exp-based evaluations; the GELU GEMMs of the adapter have K = 16..128 and are bound by this epilogue
+        f32x2 lo = f2_pack(v.x, v.y), hi = f2_pack(v.z, v.w);
+        f2_gelu_erf_poly_x2(lo, hi);
+        f2_unpack(lo, v.x, v.y);
+        f2_unpack(hi, v.z, v.w);
+      }
     } else if constexpr (ACT == ACT_RELU) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     }
