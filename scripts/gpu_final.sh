@@ -14,6 +14,6 @@ python scripts/mstcn_bench.py 2>&1 | tail -1 | tee gpurun_out/mstcn_bench.log
 if [ "${NCU:-1}" = "1" ]; then
 CMD="python bench.py --frames 800 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
 $CMD > gpurun_out/ncu_plain.log 2>&1 && \
-timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1700 -c 450 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_final.log 2>&1
+timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1540 -c 365 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_final.log 2>&1
 echo "ncu rc=$?"; wc -l gpurun_out/launches_final.csv
 fi
