@@ -259,28 +259,33 @@ def run_ours(args):
         xh, sh, fh = x.cpu().pin_memory(), seg.cpu().pin_memory(), flow.cpu().pin_memory()
         ext = lfb.LFBExtractor(model, batch_size=B, device=dev)
         out_h = torch.empty((T, 2048), dtype=torch.float32).pin_memory()
-        logits_h = torch.empty((2, 14, T), dtype=torch.float32).pin_memory()
-
-        @torch.no_grad()
-        def e2e_step():
-            f_h = ext.extract(xh, sh, fh, out=out_h)            # H2D frames/segmaps/flow, forward, D2H features
-            lg = tcn.forward_videos(f_h.to(dev, non_blocking=True), [T])
-            logits_h.copy_(lg, non_blocking=True)               # D2H phase logits (the step's result)
-            torch.cuda.synchronize()
 
         e2e_steps = max(1, min(args.steps, 3))
-        e2e_step()
+        outs_h = [out_h] + [torch.empty((T, 2048), dtype=torch.float32).pin_memory() for _ in range(e2e_steps - 1)]
+        logits_h = torch.empty((2, 14, T * e2e_steps), dtype=torch.float32).pin_memory()
+
+        @torch.no_grad()
+        def e2e_run(k):
+            # k steps = k videos through the driver-level call: one pipelined pass (H2D of every batch from pinned host memory,
+            # forward, D2H of the features), then MS-TCN over the k feature sequences and D2H of the phase logits
+            f_hs = ext.extract_videos([(xh, sh, fh)] * k, outs=outs_h[:k])
+            feats_d = torch.cat([f.to(dev, non_blocking=True) for f in f_hs], 0)
+            lg = tcn.forward_videos(feats_d, [T] * k)
+            logits_h[:, :, :T * k].copy_(lg, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_run(1)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_run(e2e_steps)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * T * e2e_steps / float(dt.item()), "unit": "frames/s",
-               "h2d_bytes_per_step": int(ext.h2d_bytes + T * 2048 * 4), "d2h_bytes_per_step": int(ext.d2h_bytes + logits_h.numel() * 4),
-               "steps": e2e_steps, "api": "LFBExtractor.extract(model=mit_b3_evp drop-in) + MultiStageModel_S.forward_videos"}
+               "h2d_bytes_per_step": int(ext.h2d_bytes // e2e_steps + T * 2048 * 4), "d2h_bytes_per_step": int(ext.d2h_bytes // e2e_steps + 2 * 14 * T * 4),
+               "steps": e2e_steps,
+               "api": "LFBExtractor.extract_videos(model=mit_b3_evp drop-in; the timed steps are videos of ONE pipelined call) + MultiStageModel_S.forward_videos"}
         del xh, sh, fh
         # same call chain from what the reference's dataset class holds after JPEG decode: uint8 250x250 frames and
         # segmentation maps + the raw fp32 RAFT field; Resize/CenterCrop/ToTensor/Normalize and the flow resize run on the GPU
@@ -293,7 +298,7 @@ def run_ours(args):
         def e2e_raw_step():
             f_h = ext.extract_raw(fr_u8, sg_u8, fl_raw, out=out_h)
             lg = tcn.forward_videos(f_h.to(dev, non_blocking=True), [T])
-            logits_h.copy_(lg, non_blocking=True)
+            logits_h[:, :, :T].copy_(lg, non_blocking=True)
             torch.cuda.synchronize()
 
         e2e_raw_step()
@@ -307,7 +312,7 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e["from_uint8_frames"] = {"value": world * T * e2e_steps / float(dt.item()), "unit": "frames/s",
                                     "h2d_bytes_per_step": int(ext.h2d_bytes + T * 2048 * 4),
-                                    "d2h_bytes_per_step": int(ext.d2h_bytes + logits_h.numel() * 4), "steps": e2e_steps,
+                                    "d2h_bytes_per_step": int(ext.d2h_bytes + 2 * 14 * T * 4), "steps": e2e_steps,
                                     "api": "LFBExtractor.extract_raw(uint8 250x250 frames + segmaps, fp32 250x250 flow) + MultiStageModel_S.forward_videos"}
         del fr_u8, sg_u8, fl_raw
 

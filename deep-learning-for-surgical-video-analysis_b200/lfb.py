@@ -83,19 +83,36 @@ class LFBExtractor:
     def extract(self, frames: torch.Tensor, segmaps: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """frames/segmaps: [N,(1,)3,H,W] fp32 HOST (pinned for full overlap), flow: [N,(1,)2,H,W] or None
         -> [N, 2048] fp32 pinned host tensor (features in input order)."""
-        N = frames.shape[0]
-        H, W = frames.shape[-2], frames.shape[-1]
-        frames = frames.reshape(N, 3, H, W)
-        segmaps = segmaps.reshape(N, 3, H, W)
-        if flow is not None:
-            flow = flow.reshape(N, 2, H, W)
-        bufs = self._staging(H, W, flow is not None)
-        if out is None:
-            out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
+        return self.extract_videos([(frames, segmaps, flow)], outs=None if out is None else [out])[0]
+
+    @torch.no_grad()
+    def extract_videos(self, videos: Sequence, outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """The reference driver's loop over videos (generate_evp_LFB.py:439-499) as ONE pipelined pass: `videos` is a sequence of
+        (frames, segmaps, flow-or-None) HOST tensors shaped as for `extract` (same H x W and flow presence for all); the copy of
+        every batch overlaps the kernels of the previous one across video boundaries, so only the very first batch of the call
+        is exposed (and only the first video is ramped up).  Returns one [T_v, 2048] fp32 pinned host tensor per video."""
+        if len(videos) == 0:
+            return []
+        H, W = videos[0][0].shape[-2], videos[0][0].shape[-1]
+        with_flow = videos[0][2] is not None
+        vids = []
+        for (fr, sg, fl) in videos:
+            N = fr.shape[0]
+            if fr.shape[-2:] != (H, W) or (fl is not None) != with_flow:
+                raise ValueError("extract_videos: all videos of a call must share H x W and the presence of flow")
+            vids.append((N, fr.reshape(N, 3, H, W), sg.reshape(N, 3, H, W), None if fl is None else fl.reshape(N, 2, H, W)))
+        bufs = self._staging(H, W, with_flow)
+        D = self.model.embedding_dim
+        if outs is None:
+            outs = [torch.empty((v[0], D), dtype=torch.float32).pin_memory() for v in vids]
         compute = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
-        starts = self._schedule(N)
-        for bi, (b0, n) in enumerate(starts):
+        batches = []
+        for vi, v in enumerate(vids):
+            sched = self._schedule(v[0]) if vi == 0 else [(b0, min(self.batch_size, v[0] - b0)) for b0 in range(0, v[0], self.batch_size)]
+            batches += [(vi, b0, n) for (b0, n) in sched]
+        for bi, (vi, b0, n) in enumerate(batches):
+            _, frames, segmaps, flow = vids[vi]
             x, s, f, ev_in, ev_free = bufs[bi % 2]
             with torch.cuda.stream(self._copy_stream):
                 if bi >= 2:
@@ -110,10 +127,10 @@ class LFBExtractor:
             compute.wait_event(ev_in)
             feats = self.model(x[:n], s[:n], None if f is None else f[:n], return_features=True)
             ev_free.record(compute)
-            out[b0:b0 + n].copy_(feats, non_blocking=True)
-            self.d2h_bytes += n * self.model.embedding_dim * 4
+            outs[vi][b0:b0 + n].copy_(feats, non_blocking=True)
+            self.d2h_bytes += n * D * 4
         compute.synchronize()
-        return out
+        return list(outs)
 
     @torch.no_grad()
     def extract_raw(self, frames_u8: torch.Tensor, segmaps_u8: torch.Tensor, flow_raw: Optional[torch.Tensor], resize: int = 250,

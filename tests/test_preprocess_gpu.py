@@ -106,3 +106,24 @@ def test_raw_extraction_equals_preprocessed_extraction():
     want = ex.extract(x, s, f)
     assert torch.equal(got, want)
     assert raw_h2d == N * (2 * h * w * 3 + h * w * 2 * 4)
+
+
+def test_extract_videos_pipelined_equals_per_video_calls():
+    """LFBExtractor.extract_videos (one pipelined pass over several videos, only the first ramped up) == extract() per video."""
+    from surgvid_b200 import synthetic
+    from surgvid_b200.lfb import LFBExtractor
+    from surgvid_b200.models.mix_transformer_evp import mit_b3_evp
+    model = mit_b3_evp()
+    model.load_state_dict(synthetic.synth_state_dict(synthetic.evp_key_shapes("mit_b3_evp"), seed=0, mode="stress"), strict=True)
+    model = model.cuda().eval()
+    vids = []
+    for i, n in enumerate((9, 4, 13)):
+        x, s, f = synthetic.synth_frames(n, seed=300 + i)
+        vids.append((x.pin_memory(), s.pin_memory(), f.pin_memory()))
+    ex = LFBExtractor(model, batch_size=4)
+    got = [t.clone() for t in ex.extract_videos(vids)]
+    assert ex.h2d_bytes == sum(v[0].shape[0] for v in vids) * 8 * 224 * 224 * 4
+    for v, g in zip(vids, got):
+        assert torch.equal(g, ex.extract(*v))
+    with pytest.raises(ValueError):
+        ex.extract_videos([vids[0], (vids[1][0], vids[1][1], None)])
