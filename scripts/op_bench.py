@@ -41,3 +41,9 @@ if which in ("all", "im2col"):
     t = torch.randn(B, 56, 56, 64, device=dev).bfloat16()
     timeit("im2col nhwc 56x56x64 k3s2p1", lambda: ops.im2col(t, 3, 2, 1), t.numel() * 2 + B * 784 * 576 * 2)
     timeit("gauss5x5 600x224x224", lambda: ops.gauss5x5(x), 2 * x.numel() * 4)
+if which in ("all", "stem"):
+    x = torch.randn(B, 3, 224, 224, device=dev)
+    w = torch.randn(64, 3, 7, 7, device=dev) * 0.1; bb = torch.randn(64, device=dev) * 0.1; g = torch.ones(64, device=dev); be = torch.zeros(64, device=dev)
+    timeit("stem conv 3->64 + LN (fp32+bf16 out)", lambda: ops.stem_conv(x, w, bb, g, be), x.numel() * 4 + B * 3136 * 64 * 6)
+    w16 = torch.randn(16, 3, 7, 7, device=dev) * 0.1; b16 = torch.randn(16, device=dev) * 0.1; g16 = torch.ones(16, device=dev); be16 = torch.zeros(16, device=dev)
+    timeit("stem conv 3->16 + LN", lambda: ops.stem_conv(x, w16, b16, g16, be16), x.numel() * 4 + B * 3136 * 16 * 6)
