@@ -3,6 +3,8 @@
 // (frame, head); K/V are streamed through shared memory in 64-key tiles with an online softmax, so the
 // [B, heads, N, N_kv] attention matrix the reference materialises never exists.  bf16 operands, fp32 softmax and
 // accumulation.  Tensor-core path: mma.sync m16n8k16 (round-1 implementation; 2.6 % of the path's FLOPs).
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace sv {
@@ -331,6 +333,150 @@ __global__ void __launch_bounds__(128) attention_resident_kv_kernel(const bf16* 
   cp_async_wait<0>();
 }
 
+// ---- 64 < N_kv <= 256 (the flow cross-attention at 224x224: N_kv = 196, head_dim 40): K and V of one (frame, head) are still small
+// enough to stay resident (dynamic shared memory); the CTA walks over its query tiles as above and, per tile, over the resident
+// 64-key tiles with the online softmax of the streaming kernel — no reloads of K/V per query tile, no load/compute serialisation.
+template <int HD>
+__global__ void __launch_bounds__(128) attention_resident_multi_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
+                                                                       const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
+                                                                       int Nq, int Nkv, float scale_log2, int tiles_per_cta, int kv_tiles) {
+  using S = AttnShape<HD>;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  bf16* Qs0 = reinterpret_cast<bf16*>(attn_smem);
+  bf16* Qs1 = Qs0 + kTile * S::LDS;
+  bf16* Ks = Qs1 + kTile * S::LDS;
+  bf16* Vs = Ks + kv_tiles * kTile * S::LDS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int tile0 = blockIdx.x * tiles_per_cta;
+  const int ntiles = min(tiles_per_cta, (Nq + kTile - 1) / kTile - tile0);
+  const bf16* qb = q + static_cast<int64_t>(b) * Nq * ldq + head * HD;
+  const bf16* kb = k + static_cast<int64_t>(b) * Nkv * ldk + head * HD;
+  const bf16* vb = v + static_cast<int64_t>(b) * Nkv * ldv + head * HD;
+  bf16* ob = o + static_cast<int64_t>(b) * Nq * ldo + head * HD;
+
+  for (int kt = 0; kt < kv_tiles; ++kt) {
+    load_tile_async<HD>(Ks + kt * kTile * S::LDS, kb, ldk, kt * kTile, Nkv);
+    load_tile_async<HD>(Vs + kt * kTile * S::LDS, vb, ldv, kt * kTile, Nkv);
+  }
+  load_tile_async<HD>(Qs0, qb, ldq, tile0 * kTile, Nq);
+  cp_async_commit();
+
+  const int mi = lane >> 3;
+  for (int j = 0; j < ntiles; ++j) {
+    const int q0 = (tile0 + j) * kTile;
+    bf16* Qc = (j & 1) ? Qs1 : Qs0;
+    if (j + 1 < ntiles) load_tile_async<HD>((j & 1) ? Qs0 : Qs1, qb, ldq, q0 + kTile, Nq);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+
+    uint32_t qf[S::KS][4];
+    {
+      const int row = warp * 16 + (mi & 1) * 8 + (lane & 7);
+#pragma unroll
+      for (int ks = 0; ks < S::KS; ++ks)
+        ldmatrix_x4(qf[ks], static_cast<uint32_t>(__cvta_generic_to_shared(Qc + row * S::LDS + ks * 16 + (mi >> 1) * 8)));
+    }
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float l_run[2] = {0.f, 0.f};
+    float oacc[S::NTO][4];
+#pragma unroll
+    for (int i = 0; i < S::NTO; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f; }
+    for (int kt = 0; kt < kv_tiles; ++kt) {
+      const bf16* Kt = Ks + kt * kTile * S::LDS;
+      const bf16* Vt = Vs + kt * kTile * S::LDS;
+      float sacc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sacc[i][0] = sacc[i][1] = sacc[i][2] = sacc[i][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < S::KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          const int key = np * 16 + (mi >> 1) * 8 + (lane & 7);
+          uint32_t kf[4];
+          ldmatrix_x4(kf, static_cast<uint32_t>(__cvta_generic_to_shared(Kt + key * S::LDS + ks * 16 + (mi & 1) * 8)));
+          mma_bf16_16816(sacc[np * 2], qf[ks], kf[0], kf[1]);
+          mma_bf16_16816(sacc[np * 2 + 1], qf[ks], kf[2], kf[3]);
+        }
+      }
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = kt * kTile + nt * 8 + t * 2 + (e & 1);
+          float sv = sacc[nt][e] * scale_log2;
+          if (key >= Nkv) sv = -INFINITY;
+          sacc[nt][e] = sv;
+          mx[e >> 1] = fmaxf(mx[e >> 1], sv);
+        }
+      }
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);  // finite: every key tile holds >= 1 valid key
+        corr[r] = exp2f(m_run[r] - m_new);
+        m_run[r] = m_new;
+        l_run[r] *= corr[r];
+      }
+#pragma unroll
+      for (int i = 0; i < S::NTO; ++i) {
+        oacc[i][0] *= corr[0]; oacc[i][1] *= corr[0];
+        oacc[i][2] *= corr[1]; oacc[i][3] *= corr[1];
+      }
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = exp2f(sacc[nt][0] - m_run[0]), p1 = exp2f(sacc[nt][1] - m_run[0]);
+        const float p2 = exp2f(sacc[nt][2] - m_run[1]), p3 = exp2f(sacc[nt][3] - m_run[1]);
+        l_run[0] += p0 + p1;
+        l_run[1] += p2 + p3;
+        const int kk = nt >> 1;
+        if ((nt & 1) == 0) { pf[kk][0] = pack_bf16x2(p0, p1); pf[kk][1] = pack_bf16x2(p2, p3); }
+        else               { pf[kk][2] = pack_bf16x2(p0, p1); pf[kk][3] = pack_bf16x2(p2, p3); }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int dp = 0; dp < S::NTO / 2; ++dp) {
+          const int key = kk * 16 + (mi & 1) * 8 + (lane & 7);
+          uint32_t vf[4];
+          ldmatrix_x4_trans(vf, static_cast<uint32_t>(__cvta_generic_to_shared(Vt + key * S::LDS + (dp * 2 + (mi >> 1)) * 8)));
+          mma_bf16_16816(oacc[dp * 2], pf[kk], vf[0], vf[1]);
+          mma_bf16_16816(oacc[dp * 2 + 1], pf[kk], vf[2], vf[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+      l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < S::NTO; ++i) {
+      const int col = i * 8 + t * 2;
+      *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g) * S::LDS + col) = pack_bf16x2(oacc[i][0] * inv0, oacc[i][1] * inv0);
+      *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g + 8) * S::LDS + col) = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
+    }
+    __syncwarp();
+    constexpr int CH = HD / 8;
+    for (int i = lane; i < 16 * CH; i += 32) {
+      const int r = i / CH, c = i % CH;
+      const int row = q0 + warp * 16 + r;
+      if (row < Nq)
+        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+}
+
 template <int HD>
 int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads,
                 int Nq, int Nkv, float scale, cudaStream_t st) {
@@ -344,6 +490,22 @@ int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf
     dim3 grid(ceil_div(qtiles, tpc), heads, B);
     attention_resident_kv_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2, tpc);
     return launch_status("attention_resident_kv_kernel");
+  }
+  if (Nkv <= 4 * kTile && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    using S = AttnShape<HD>;
+    const int kv_tiles = ceil_div(Nkv, kTile);
+    const int smem = (2 + 2 * kv_tiles) * kTile * S::LDS * static_cast<int>(sizeof(bf16));
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+      attr_err = cudaFuncSetAttribute(attention_resident_multi_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (2 + 2 * 4) * kTile * S::LDS * static_cast<int>(sizeof(bf16)));
+    });
+    if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(attention): ") + cudaGetErrorString(attr_err));
+    const int tpc = std::min(qtiles, 8);
+    dim3 grid(ceil_div(qtiles, tpc), heads, B);
+    attention_resident_multi_kernel<HD><<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2, tpc, kv_tiles);
+    return launch_status("attention_resident_multi_kernel");
   }
   dim3 grid(qtiles, heads, B);
   attention_kernel<HD><<<grid, 128, 0, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2);
