@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(128) attention_resident_kv_kernel(const bf16* 
     cp_async_wait<1>();  // everything except the group just committed has landed (K, V, Q(j))
     __syncthreads();
 
+    if (q0 + warp * 16 < Nq) {   // a warp whose 16 rows lie beyond the last query (196 = 3 x 64 + 4) has nothing to do for this tile
     uint32_t qf[S::KS][4];
     {
       const int row = warp * 16 + (mi & 1) * 8 + (lane & 7);
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(128) attention_resident_kv_kernel(const bf16* 
       if (row < Nq)
         *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
     }
+    }
     __syncthreads();  // Qc may be refilled by the prefetch issued at the top of the next-but-one iteration
   }
   cp_async_wait<0>();
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(128) attention_resident_multi_kernel(const bf1
     cp_async_wait<1>();
     __syncthreads();
 
+    if (q0 + warp * 16 < Nq) {
     uint32_t qf[S::KS][4];
     {
       const int row = warp * 16 + (mi & 1) * 8 + (lane & 7);
@@ -471,6 +474,7 @@ __global__ void __launch_bounds__(128) attention_resident_multi_kernel(const bf1
       const int row = q0 + warp * 16 + r;
       if (row < Nq)
         *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+    }
     }
     __syncthreads();
   }
