@@ -37,12 +37,22 @@ struct AttnShape {
 template <int HD>
 __device__ __forceinline__ void load_tile(bf16* __restrict__ dst, const bf16* __restrict__ src, int64_t ld, int r0, int rows_total) {
   using S = AttnShape<HD>;
-  constexpr int CH = S::HDP / 8;
-  for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
-    const int r = i / CH, c = i % CH;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r0 + r < rows_total && c * 8 < HD) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r0 + r) * ld + c * 8));
-    *reinterpret_cast<uint4*>(dst + r * S::LDS + c * 8) = v;
+  if constexpr (HD % 8 == 0) {
+    constexpr int CH = S::HDP / 8;
+    for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+      const int r = i / CH, c = i % CH;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (r0 + r < rows_total && c * 8 < HD) v = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r0 + r) * ld + c * 8));
+      *reinterpret_cast<uint4*>(dst + r * S::LDS + c * 8) = v;
+    }
+  } else {  // head_dim 20 (mit_b0_evp flow cross-attention): a head starts 8-byte aligned only, so move 8-byte chunks
+    constexpr int CH = S::HDP / 4;
+    for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+      const int r = i / CH, c = i % CH;
+      uint2 v = make_uint2(0u, 0u);
+      if (r0 + r < rows_total && c * 4 < HD) v = __ldg(reinterpret_cast<const uint2*>(src + static_cast<int64_t>(r0 + r) * ld + c * 4));
+      *reinterpret_cast<uint2*>(dst + r * S::LDS + c * 4) = v;
+    }
   }
 }
 
@@ -194,6 +204,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
   const int bytes = valid ? 16 : 0;  // src-size 0 -> zero fill
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -201,12 +216,22 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int HD>
 __device__ __forceinline__ void load_tile_async(bf16* __restrict__ dst, const bf16* __restrict__ src, int64_t ld, int r0, int rows_total) {
   using S = AttnShape<HD>;
-  constexpr int CH = S::HDP / 8;
-  for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
-    const int r = i / CH, c = i % CH;
-    const bool ok = (r0 + r < rows_total) && (c * 8 < HD);
-    const bf16* g = ok ? src + static_cast<int64_t>(r0 + r) * ld + c * 8 : src;
-    cp_async16(dst + r * S::LDS + c * 8, g, ok);
+  if constexpr (HD % 8 == 0) {
+    constexpr int CH = S::HDP / 8;
+    for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+      const int r = i / CH, c = i % CH;
+      const bool ok = (r0 + r < rows_total) && (c * 8 < HD);
+      const bf16* g = ok ? src + static_cast<int64_t>(r0 + r) * ld + c * 8 : src;
+      cp_async16(dst + r * S::LDS + c * 8, g, ok);
+    }
+  } else {
+    constexpr int CH = S::HDP / 4;
+    for (int i = threadIdx.x; i < kTile * CH; i += blockDim.x) {
+      const int r = i / CH, c = i % CH;
+      const bool ok = (r0 + r < rows_total) && (c * 4 < HD);
+      const bf16* g = ok ? src + static_cast<int64_t>(r0 + r) * ld + c * 4 : src;
+      cp_async8(dst + r * S::LDS + c * 4, g, ok);
+    }
   }
 }
 
@@ -322,12 +347,22 @@ __global__ void __launch_bounds__(128) attention_resident_kv_kernel(const bf16* 
       *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g + 8) * S::LDS + col) = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
     }
     __syncwarp();
-    constexpr int CH = HD / 8;  // 16-byte chunks per output row
-    for (int i = lane; i < 16 * CH; i += 32) {
-      const int r = i / CH, c = i % CH;
-      const int row = q0 + warp * 16 + r;
-      if (row < Nq)
-        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+    if constexpr (HD % 8 == 0) {
+      constexpr int CH = HD / 8;  // 16-byte chunks per output row
+      for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i % CH;
+        const int row = q0 + warp * 16 + r;
+        if (row < Nq)
+          *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+      }
+    } else {
+      constexpr int CH = HD / 4;  // 8-byte chunks
+      for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i % CH;
+        const int row = q0 + warp * 16 + r;
+        if (row < Nq)
+          *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(row) * ldo + c * 4) = *reinterpret_cast<const uint2*>(Qc + (warp * 16 + r) * S::LDS + c * 4);
+      }
     }
     }
     __syncthreads();  // Qc may be refilled by the prefetch issued at the top of the next-but-one iteration
@@ -468,12 +503,22 @@ __global__ void __launch_bounds__(128) attention_resident_multi_kernel(const bf1
       *reinterpret_cast<uint32_t*>(Qc + (warp * 16 + g + 8) * S::LDS + col) = pack_bf16x2(oacc[i][2] * inv1, oacc[i][3] * inv1);
     }
     __syncwarp();
-    constexpr int CH = HD / 8;
-    for (int i = lane; i < 16 * CH; i += 32) {
-      const int r = i / CH, c = i % CH;
-      const int row = q0 + warp * 16 + r;
-      if (row < Nq)
-        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+    if constexpr (HD % 8 == 0) {
+      constexpr int CH = HD / 8;  // 16-byte chunks per output row
+      for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i % CH;
+        const int row = q0 + warp * 16 + r;
+        if (row < Nq)
+          *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(row) * ldo + c * 8) = *reinterpret_cast<const uint4*>(Qc + (warp * 16 + r) * S::LDS + c * 8);
+      }
+    } else {
+      constexpr int CH = HD / 4;  // 8-byte chunks
+      for (int i = lane; i < 16 * CH; i += 32) {
+        const int r = i / CH, c = i % CH;
+        const int row = q0 + warp * 16 + r;
+        if (row < Nq)
+          *reinterpret_cast<uint2*>(ob + static_cast<int64_t>(row) * ldo + c * 4) = *reinterpret_cast<const uint2*>(Qc + (warp * 16 + r) * S::LDS + c * 4);
+      }
     }
     }
     __syncthreads();
@@ -486,7 +531,7 @@ int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf
                 int Nq, int Nkv, float scale, cudaStream_t st) {
   const float scale_log2 = scale * 1.4426950408889634f;
   const int qtiles = ceil_div(Nq, kTile);
-  if (Nkv <= kTile && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+  if (Nkv <= kTile && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {  // (heads of 20 columns stay 8-byte aligned under these)
     // enough CTAs to fill the machine a few times over, but as many query tiles per CTA as that allows (K/V loaded once per CTA)
     int tpc = 1;
     while (tpc < 8 && tpc < qtiles && static_cast<long long>(ceil_div(qtiles, tpc * 2)) * heads * B >= 4LL * 148 * 4) tpc *= 2;
@@ -525,10 +570,11 @@ int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, con
   SV_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention leading dims must keep 16-byte row alignment");
   SV_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0, "attention operand alignment");
   switch (hd) {
+    case 20: return attn_launch<20>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
     case 32: return attn_launch<32>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
     case 40: return attn_launch<40>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
     case 64: return attn_launch<64>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
-    default: return fail(SV_ERR_UNSUPPORTED, "attention head_dim must be 32, 40 or 64");
+    default: return fail(SV_ERR_UNSUPPORTED, "attention head_dim must be 20, 32, 40 or 64");
   }
 }
 

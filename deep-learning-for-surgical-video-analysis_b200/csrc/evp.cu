@@ -518,8 +518,8 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
   if (with_flow) {  // MotionGuidedCrossAttention is nn.MultiheadAttention(dim, 8 heads) (mix_transformer_evp.py:866-870)
     for (int j = 2; j < 4; ++j) {
       const int hd = c.embed_dims[j] / 8;
-      if (c.embed_dims[j] % 8 != 0 || (hd != 32 && hd != 40 && hd != 64))
-        return fail(SV_ERR_UNSUPPORTED, "evp: flow cross-attention head_dim (C/8) must be 32, 40 or 64 (mit_b0_evp with flow is not supported)");
+      if (c.embed_dims[j] % 8 != 0 || (hd != 20 && hd != 32 && hd != 40 && hd != 64))
+        return fail(SV_ERR_UNSUPPORTED, "evp: flow cross-attention head_dim (C/8) must be 20, 32, 40 or 64");
     }
   }
   const int E = c.embedding_dim;
@@ -879,7 +879,7 @@ size_t sv_evp_workspace_bytes(const sv_evp_handle* h, int32_t micro_batch, int32
   const bool flow_ok = [&] {
     for (int j = 2; j < 4; ++j) {
       const int hd = h->cfg.embed_dims[j] / 8;
-      if (h->cfg.embed_dims[j] % 8 != 0 || (hd != 32 && hd != 40 && hd != 64)) return false;
+      if (h->cfg.embed_dims[j] % 8 != 0 || (hd != 20 && hd != 32 && hd != 40 && hd != 64)) return false;
     }
     return true;
   }();

@@ -129,12 +129,12 @@ def test_reload_state_dict_repacks():
     assert not torch.allclose(a, b) and torch.equal(a, c)
 
 
-@pytest.mark.parametrize("variant,hw,with_flow", [("mit_b0_evp", (224, 224), False), ("mit_b0_evp", (96, 160), False), ("mit_b2_evp", (128, 128), True),
+@pytest.mark.parametrize("variant,hw,with_flow", [("mit_b0_evp", (224, 224), True), ("mit_b0_evp", (96, 160), False), ("mit_b2_evp", (128, 128), True),
                                                   ("mit_b1_evp", (224, 224), True)])
 def test_other_variants_match_oracle(variant, hw, with_flow):
     """The reference exports mit_b0..b5_evp (mix_transformer_evp.py:897-939); the LFB driver uses b3, the others share the code path.
-    b0 has different widths everywhere (32/64/160/256; adapter 8/16/40/64; head_dim 32) — its flow cross-attention would have
-    head_dim 20, which the attention kernel does not implement, so b0 runs without flow; b1/b2 differ in depth only."""
+    b0 has different widths everywhere (32/64/160/256; adapter 8/16/40/64; block head_dim 32, flow cross-attention head_dim 20 and 32);
+    b1/b2 differ in depth only."""
     from surgvid_b200.models import mix_transformer_evp as M
     cfg = S.EVP_CONFIGS[variant]
     m = getattr(M, variant)()
@@ -148,9 +148,6 @@ def test_other_variants_match_oracle(variant, hw, with_flow):
     with torch.no_grad():
         out = m(x.to(DEV), seg.to(DEV), None if flow is None else flow.to(DEV), return_features=True)
     _check(out, ref, f"{variant} {hw[0]}x{hw[1]} flow={with_flow} vs oracle")
-    if variant == "mit_b0_evp":
-        with pytest.raises(RuntimeError, match="head_dim"):
-            m(x.to(DEV), seg.to(DEV), torch.zeros(3, 2, hw[0], hw[1], device=DEV), return_features=True)
 
 
 def test_full_size_video_properties():

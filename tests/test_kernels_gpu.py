@@ -138,7 +138,8 @@ def test_dwconv3x3_gelu(shape):
 
 
 @pytest.mark.parametrize("cfg", [(3, 1, 3136, 49, 64), (2, 2, 784, 49, 64), (2, 5, 196, 49, 64), (3, 8, 49, 49, 64), (2, 8, 196, 196, 40),
-                                 (1, 1, 1000, 390, 64), (2, 8, 405, 405, 64), (2, 5, 160, 70, 32), (1, 2, 5, 3, 64)])
+                                 (1, 1, 1000, 390, 64), (2, 8, 405, 405, 64), (2, 5, 160, 70, 32), (1, 2, 5, 3, 64),
+                                 (2, 8, 196, 196, 20), (3, 8, 49, 49, 20), (1, 8, 300, 330, 20)])   # head_dim 20: mit_b0_evp flow cross-attention
 def test_attention(cfg):
     B, heads, Nq, Nkv, hd = cfg
     C = heads * hd
