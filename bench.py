@@ -255,6 +255,7 @@ def run_ours(args):
 
     # ---- end-to-end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
+    numa_cpus = lfb.bind_to_gpu_numa_node(local) if world > 1 else None   # pinned staging memory on the GPU's own NUMA node
     if not args.no_e2e:
         xh, sh, fh = x.cpu().pin_memory(), seg.cpu().pin_memory(), flow.cpu().pin_memory()
         ext = lfb.LFBExtractor(model, batch_size=B, device=dev)
@@ -284,7 +285,7 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * T * e2e_steps / float(dt.item()), "unit": "frames/s",
                "h2d_bytes_per_step": int(ext.h2d_bytes // e2e_steps + T * 2048 * 4), "d2h_bytes_per_step": int(ext.d2h_bytes // e2e_steps + 2 * 14 * T * 4),
-               "steps": e2e_steps,
+               "steps": e2e_steps, "host_cores_bound": (len(numa_cpus) if numa_cpus else None),
                "api": "LFBExtractor.extract_videos(model=mit_b3_evp drop-in; the timed steps are videos of ONE pipelined call) + MultiStageModel_S.forward_videos"}
         del xh, sh, fh
         # same call chain from what the reference's dataset class holds after JPEG decode: uint8 250x250 frames and
@@ -295,25 +296,25 @@ def run_ours(args):
         fl_raw = (2.0 * torch.randn((T, 250, 250, 2), generator=g)).pin_memory()
 
         @torch.no_grad()
-        def e2e_raw_step():
-            f_h = ext.extract_raw(fr_u8, sg_u8, fl_raw, out=out_h)
-            lg = tcn.forward_videos(f_h.to(dev, non_blocking=True), [T])
-            logits_h[:, :, :T].copy_(lg, non_blocking=True)
+        def e2e_raw_run(k):
+            f_hs = ext.extract_raw_videos([(fr_u8, sg_u8, fl_raw)] * k, outs=outs_h[:k])
+            feats_d = torch.cat([f.to(dev, non_blocking=True) for f in f_hs], 0)
+            lg = tcn.forward_videos(feats_d, [T] * k)
+            logits_h[:, :, :T * k].copy_(lg, non_blocking=True)
             torch.cuda.synchronize()
 
-        e2e_raw_step()
+        e2e_raw_run(1)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_raw_step()
+        e2e_raw_run(e2e_steps)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e["from_uint8_frames"] = {"value": world * T * e2e_steps / float(dt.item()), "unit": "frames/s",
-                                    "h2d_bytes_per_step": int(ext.h2d_bytes + T * 2048 * 4),
-                                    "d2h_bytes_per_step": int(ext.d2h_bytes + 2 * 14 * T * 4), "steps": e2e_steps,
-                                    "api": "LFBExtractor.extract_raw(uint8 250x250 frames + segmaps, fp32 250x250 flow) + MultiStageModel_S.forward_videos"}
+                                    "h2d_bytes_per_step": int(ext.h2d_bytes // e2e_steps + T * 2048 * 4),
+                                    "d2h_bytes_per_step": int(ext.d2h_bytes // e2e_steps + 2 * 14 * T * 4), "steps": e2e_steps,
+                                    "api": "LFBExtractor.extract_raw_videos(uint8 250x250 frames + segmaps, fp32 250x250 flow; one pipelined call) + MultiStageModel_S.forward_videos"}
         del fr_u8, sg_u8, fl_raw
 
     # ---- per-kernel-class device timing (CUDA events around every launch, on the launching stream; untimed extra pass)

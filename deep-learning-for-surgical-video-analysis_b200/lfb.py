@@ -16,6 +16,28 @@ import numpy as np
 import torch
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[List[int]]:
+    """Restrict this process to the CPU cores that are local to GPU `device_index` (NVML's CPU affinity for the device), so that the
+    pinned staging buffers it allocates afterwards are first-touched on that NUMA node and every rank's H2D stream reads local memory.
+    With 8 ranks feeding 8 GPUs from one socket's memory the host side, not PCIe, limits the end-to-end rate.  Returns the core
+    list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1 and w * 64 + b < n_cpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def lpt_assign(lengths: Sequence[int], n_ranks: int) -> List[List[int]]:
     """Longest-processing-time-first assignment of videos to ranks. Returns per-rank video indices, ascending."""
     loads = [0] * n_ranks
@@ -139,9 +161,21 @@ class LFBExtractor:
         frames/segmaps uint8 [N, H, W, 3] HOST, flow float32 [N, Hf, Wf, 2] HOST (raw RAFT field) or None.  The
         Resize/CenterCrop/ToTensor/Normalize and the flow resize+rescale run on the GPU (preprocess.FramePreprocessor), so
         uint8 frames cross PCIe instead of normalised fp32."""
+        return self.extract_raw_videos([(frames_u8, segmaps_u8, flow_raw)], resize=resize, crop=crop, outs=None if out is None else [out])[0]
+
+    @torch.no_grad()
+    def extract_raw_videos(self, videos: Sequence, resize: int = 250, crop: int = 224,
+                           outs: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """`extract_videos` for raw inputs: `videos` is a sequence of (frames_u8, segmaps_u8, flow_raw-or-None) HOST tensors (one frame
+        size and one flow size per call); one pipelined pass, only the first video ramped up."""
         from .preprocess import FramePreprocessor
-        N, H, W = frames_u8.shape[0], frames_u8.shape[1], frames_u8.shape[2]
-        fhw = None if flow_raw is None else (flow_raw.shape[1], flow_raw.shape[2])
+        if len(videos) == 0:
+            return []
+        H, W = videos[0][0].shape[1], videos[0][0].shape[2]
+        fhw = None if videos[0][2] is None else (videos[0][2].shape[1], videos[0][2].shape[2])
+        for (fr, sg, fl) in videos:
+            if (fr.shape[1], fr.shape[2]) != (H, W) or (None if fl is None else (fl.shape[1], fl.shape[2])) != fhw:
+                raise ValueError("extract_raw_videos: all videos of a call must share the frame size and the flow size")
         key = (H, W, fhw, resize, crop)
         if getattr(self, "_prep_key", None) != key:
             self._prep = FramePreprocessor((H, W), flow_hw=fhw, resize=resize, crop=crop)
@@ -155,13 +189,19 @@ class LFBExtractor:
             self._pre_out = (torch.empty((self.batch_size, 3, crop, crop), dtype=torch.float32, device=self.device),
                              torch.empty((self.batch_size, 3, crop, crop), dtype=torch.float32, device=self.device),
                              None if fhw is None else torch.empty((self.batch_size, 2, crop, crop), dtype=torch.float32, device=self.device))
-        if out is None:
-            out = torch.empty((N, self.model.embedding_dim), dtype=torch.float32).pin_memory()
+        D = self.model.embedding_dim
+        if outs is None:
+            outs = [torch.empty((v[0].shape[0], D), dtype=torch.float32).pin_memory() for v in videos]
         compute = torch.cuda.current_stream(self.device)
         self.h2d_bytes = self.d2h_bytes = 0
-        starts = self._schedule(N)
+        batches = []
+        for vi, v in enumerate(videos):
+            N = v[0].shape[0]
+            sched = self._schedule(N) if vi == 0 else [(b0, min(self.batch_size, N - b0)) for b0 in range(0, N, self.batch_size)]
+            batches += [(vi, b0, n) for (b0, n) in sched]
         x, s, f = self._pre_out
-        for bi, (b0, n) in enumerate(starts):
+        for bi, (vi, b0, n) in enumerate(batches):
+            frames_u8, segmaps_u8, flow_raw = videos[vi]
             fu, su, fl, ev_in, ev_free = self._raw[bi % 2]
             with torch.cuda.stream(self._copy_stream):
                 if bi >= 2:
@@ -180,10 +220,10 @@ class LFBExtractor:
                 self._prep.flow(fl[:n], out=f[:n])
             ev_free.record(compute)  # the raw staging buffers are free once the transforms have run
             feats = self.model(x[:n], s[:n], None if fl is None else f[:n], return_features=True)
-            out[b0:b0 + n].copy_(feats, non_blocking=True)
-            self.d2h_bytes += n * self.model.embedding_dim * 4
+            outs[vi][b0:b0 + n].copy_(feats, non_blocking=True)
+            self.d2h_bytes += n * D * 4
         compute.synchronize()
-        return out
+        return list(outs)
 
     def extract_float64(self, frames, segmaps, flow) -> np.ndarray:
         """Same values as `extract`, as the float64 ndarray the reference pickles (generate_evp_LFB.py:513-520)."""
