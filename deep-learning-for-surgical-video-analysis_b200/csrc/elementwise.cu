@@ -265,49 +265,42 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
 // ------------------------------------------------------------------------------------------ Gaussian 5x5 (reflect pad 2)
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-// one thread = 4 horizontally adjacent outputs of one row; block (32, 8), grid (column groups, row groups, planes) — no index
-// divisions.  Interior threads read each of the 5 source rows as three aligned float4 (columns w0-4 .. w0+7) and write one
-// float4; threads touching the left/right border take the scalar reflect path.
-__global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int vec) {
-  const int w0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int h = blockIdx.y * 8 + threadIdx.y;
-  if (w0 >= W || h >= H) return;
+// 32x32 output tile per block (256 threads): the 36x36 reflect-padded input tile goes to shared memory once (coalesced rows), the
+// separable filter runs as a horizontal pass into a second shared tile and a vertical pass out of it — 10 FMAs and ~1.3 global
+// loads per output instead of 25+ cached loads (the direct version was bound by L1 traffic at 1.4 TB/s).  Same FMA order as the
+// direct form (sum over dx first, then over dy), so results are bit-identical to it.
+constexpr int kGT = 32;   // tile edge
+__global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W) {
+  __shared__ float tin[kGT + 4][kGT + 4 + 1];
+  __shared__ float tmp[kGT + 4][kGT + 1];
+  const int x0 = blockIdx.x * kGT, y0 = blockIdx.y * kGT;
   const int64_t pl = blockIdx.z;
   const float* src = x + pl * H * W;
   const float k1[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};  // outer(k1,k1) == [1 4 6 4 1]^2 / 256 exactly
-  const bool fast = vec && w0 >= 4 && w0 + 8 <= W;   // vec: W % 4 == 0 and 16-byte aligned planes
-  int cols[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) cols[j] = reflect_idx(min(w0 + j - 2, W + 1), W);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int dy = 0; dy < 5; ++dy) {
-    const float* rowp = src + static_cast<int64_t>(reflect_idx(h + dy - 2, H)) * W;
-    float v[8];
-    if (fast) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(rowp + w0 - 4));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(rowp + w0));
-      const float4 c = __ldg(reinterpret_cast<const float4*>(rowp + w0 + 4));
-      v[0] = a.z; v[1] = a.w; v[2] = b.x; v[3] = b.y; v[4] = b.z; v[5] = b.w; v[6] = c.x; v[7] = c.y;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = __ldg(rowp + cols[j]);
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      float r = 0.f;
-#pragma unroll
-      for (int dx = 0; dx < 5; ++dx) r = fmaf(v[o + dx], k1[dx], r);
-      acc[o] = fmaf(r, k1[dy], acc[o]);
-    }
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  for (int i = tid; i < (kGT + 4) * (kGT + 4); i += 256) {
+    const int r = i / (kGT + 4), c = i - r * (kGT + 4);
+    const int gy = reflect_idx(min(y0 + r - 2, H + 1), H), gx = reflect_idx(min(x0 + c - 2, W + 1), W);
+    tin[r][c] = __ldg(src + static_cast<int64_t>(gy) * W + gx);
   }
-  float* dst = out + (pl * H + h) * W + w0;
-  if (vec) {
-    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  } else {
+  __syncthreads();
+  for (int i = tid; i < (kGT + 4) * kGT; i += 256) {
+    const int r = i / kGT, c = i - r * kGT;
+    float v = 0.f;
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
-      if (w0 + o < W) dst[o] = acc[o];
+    for (int dx = 0; dx < 5; ++dx) v = fmaf(tin[r][c + dx], k1[dx], v);
+    tmp[r][c] = v;
+  }
+  __syncthreads();
+  const int gx = x0 + threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < kGT / 8; ++j) {
+    const int r = threadIdx.y + j * 8;
+    const int gy = y0 + r;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) acc = fmaf(tmp[r + dy][threadIdx.x], k1[dy], acc);
+    if (gx < W && gy < H) out[(pl * H + gy) * W + gx] = acc;
   }
 }
 
@@ -450,10 +443,9 @@ int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, in
 
 int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st) {
   SV_CHECK(H >= 3 && W >= 3, "gauss5x5 needs H,W >= 3 (reflect pad 2)");
-  SV_CHECK(planes >= 1 && planes <= 65535 && ceil_div(H, 8) <= 65535, "gauss5x5 grid limits");
-  const int vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-  dim3 grid(static_cast<unsigned>(ceil_div(ceil_div(W, 4), 32)), static_cast<unsigned>(ceil_div(H, 8)), static_cast<unsigned>(planes));
-  gauss5x5_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, H, W, vec);
+  SV_CHECK(planes >= 1 && planes <= 65535 && ceil_div(H, kGT) <= 65535, "gauss5x5 grid limits");
+  dim3 grid(static_cast<unsigned>(ceil_div(W, kGT)), static_cast<unsigned>(ceil_div(H, kGT)), static_cast<unsigned>(planes));
+  gauss5x5_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, H, W);
   return launch_status("gauss5x5_kernel");
 }
 
