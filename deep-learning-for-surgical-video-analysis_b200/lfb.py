@@ -63,6 +63,18 @@ def gather_in_video_order(per_rank_blocks: Sequence[Sequence[np.ndarray]], assig
     return np.concatenate(slots, axis=0)
 
 
+def ramp_schedule(n_frames: int, batch_size: int, ramp_start: int) -> List[tuple]:
+    """(first frame, count) of the batches of one call: small first batches so the kernels start while the bulk of the input is
+    still crossing PCIe (only the first copy of a call is not overlapped with compute), doubling up to batch_size."""
+    starts, b0, ramp = [], 0, max(1, int(ramp_start))
+    while b0 < n_frames:
+        n = min(ramp, batch_size, n_frames - b0)
+        starts.append((b0, n))
+        b0 += n
+        ramp *= 2
+    return starts
+
+
 class LFBExtractor:
     """End-to-end feature extraction from HOST buffers through the drop-in model (the call a user of the reference
     makes, with the reference's batch size of 200 by default: generate_evp_LFB.py:36 `--val`)."""
@@ -79,15 +91,7 @@ class LFBExtractor:
         self.d2h_bytes = 0
 
     def _schedule(self, N: int):
-        """Ramp-up schedule: small first batches so the kernels start while the bulk of the input is still crossing PCIe
-        (only the first copy of a call is not overlapped with compute), doubling up to batch_size."""
-        starts, b0, ramp = [], 0, self.ramp_start
-        while b0 < N:
-            n = min(ramp, self.batch_size, N - b0)
-            starts.append((b0, n))
-            b0 += n
-            ramp *= 2
-        return starts
+        return ramp_schedule(N, self.batch_size, self.ramp_start)
 
     def _staging(self, H, W, with_flow):
         key = (H, W, with_flow)

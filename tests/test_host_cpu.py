@@ -136,3 +136,26 @@ def test_gemm_tile_picker_is_legal():
     for C in EVP_CONFIGS["mit_b3_evp"]["embed_dims"]:
         for N in (C // 4, C, 2 * C, 4 * C, 2048):
             assert N % 8 == 0
+
+
+def test_ramp_schedule_covers_every_frame_once():
+    from surgvid_b200.lfb import ramp_schedule
+    for n, b, r in [(2300, 800, 100), (2300, 200, 25), (7, 4, 1), (1, 800, 100), (800, 800, 800), (0, 800, 100)]:
+        sched = ramp_schedule(n, b, r)
+        assert sum(c for _, c in sched) == n
+        pos = 0
+        for b0, c in sched:
+            assert b0 == pos and 1 <= c <= b
+            pos += c
+        if n >= r:
+            assert sched[0][1] == min(r, b)
+    assert ramp_schedule(2300, 800, 100) == [(0, 100), (100, 200), (300, 400), (700, 800), (1500, 800)]
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    import os
+    from surgvid_b200.lfb import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), list)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
