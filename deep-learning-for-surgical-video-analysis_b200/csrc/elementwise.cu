@@ -377,10 +377,12 @@ int launch_layernorm_patch(const float* x, const float* gamma, const float* beta
   const int nvec = C / 4;
 #define SV_LN(L, N) return ln_launch<L, N>(x, gamma, beta, eps, rows, C, out_f32, out_bf16, out_patch, pH, pW, psr, st)
   // exact lane mappings first (every slot a real element): the model's widths 16/32/64/128/256/512 and 40/80/160/320
-  if (nvec == 4) SV_LN(4, 1);
-  if (nvec == 8) SV_LN(8, 1);
-  if (nvec == 16) SV_LN(16, 1);
-  if (nvec == 32) SV_LN(16, 2);
+  // (narrow rows: fewer lanes per row and two float4 per lane — the fixed per-thread work, shuffles and patch index math are
+  //  amortised over more bytes: 64 -> 49 us for 627200 x 64, 28 -> 26 us for 156800 x 128; ten float4 per lane for C = 320 spills)
+  if (nvec == 4) SV_LN(2, 2);
+  if (nvec == 8) SV_LN(4, 2);
+  if (nvec == 16) SV_LN(8, 2);
+  if (nvec == 32) SV_LN(8, 4);
   if (nvec == 64) SV_LN(16, 4);
   if (nvec == 128) SV_LN(32, 4);
   if (nvec == 10) SV_LN(2, 5);
