@@ -1,5 +1,7 @@
 // Error plumbing and device queries shared by every translation unit of libsurgvid.
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -26,6 +28,24 @@ int device_sm_count() {
   cached_dev = dev;
   cached = n;
   return n;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: remember which (device, kernel, bytes) were configured and
+// never cache a failure, so a handle created on a second GPU of the same process opts its kernels in again.
+int ensure_dynamic_smem(const void* fn, int bytes) {
+  if (bytes <= 48 * 1024) return SV_OK;
+  int dev = 0;
+  SV_CUDA_OK(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> configured;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, fn);
+  auto it = configured.find(key);
+  if (it != configured.end() && it->second >= bytes) return SV_OK;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e));
+  configured[key] = bytes;
+  return SV_OK;
 }
 
 }  // namespace sv

@@ -544,13 +544,7 @@ int attn_launch(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf
     using S = AttnShape<HD>;
     const int kv_tiles = ceil_div(Nkv, kTile);
     const int smem = (2 + 2 * kv_tiles) * kTile * S::LDS * static_cast<int>(sizeof(bf16));
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-      attr_err = cudaFuncSetAttribute(attention_resident_multi_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (2 + 2 * 4) * kTile * S::LDS * static_cast<int>(sizeof(bf16)));
-    });
-    if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(attention): ") + cudaGetErrorString(attr_err));
+    SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_resident_multi_kernel<HD>), (2 + 2 * 4) * kTile * S::LDS * static_cast<int>(sizeof(bf16))));
     const int tpc = std::min(qtiles, 8);
     dim3 grid(ceil_div(qtiles, tpc), heads, B);
     attention_resident_multi_kernel<HD><<<grid, 128, smem, st>>>(q, ldq, k, ldk, v, ldv, o, ldo, Nq, Nkv, scale_log2, tpc, kv_tiles);

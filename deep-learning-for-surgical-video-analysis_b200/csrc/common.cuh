@@ -40,6 +40,8 @@ inline int launch_status(const char* what) {
 }
 
 int device_sm_count();
+// opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (idempotent, thread-safe, failures are not cached)
+int ensure_dynamic_smem(const void* fn, int bytes);
 
 typedef __nv_bfloat16 bf16;
 

@@ -204,11 +204,8 @@ int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, i
 }
 
 int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
   constexpr int smem_bytes = kStages * kTileBytes + 128;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(dwconv3x3_gelu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); });
-  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(dwconv): ") + cudaGetErrorString(attr_err));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(dwconv3x3_gelu_tma_kernel), smem_bytes));
   DwParams p;
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tw = plan.tw;

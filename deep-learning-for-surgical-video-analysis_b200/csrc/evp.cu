@@ -91,6 +91,8 @@ struct Plan {
   int n = 0, H = 0, W = 0;
   bool with_flow = false;
   void* ws = nullptr;
+  size_t need = 0;        // workspace bytes this plan addresses
+  uint64_t last_use = 0;  // for eviction
   std::vector<Op> ops;
   std::map<std::string, Tap> taps;
   double gemm_flops = 0.0;
@@ -110,6 +112,8 @@ struct Arena {
     return p;
   }
 };
+
+constexpr size_t kMaxPlans = 16;  // distinct (micro-batch, H, W, flow) schedules kept per handle
 
 struct StageGeom {
   int H, W, N, C, heads, sr, Hk, Wk, Nkv, hidden, Cp;
@@ -132,7 +136,8 @@ struct sv_evp {
   sv::Lin head_fuse;   // [E, 4E] (BN scale folded), bias = BN shift
   sv::Lin head_fold;   // [E, sum C_i] when cfg.fold_head
   size_t fc_w[2][2] = {{0, 0}, {0, 0}}, fc_b[2][2] = {{0, 0}, {0, 0}};  // fp32 classifier heads: [fc|fc_ant][layer]
-  std::map<long long, std::unique_ptr<sv::Plan>> plans;
+  std::map<long long, std::unique_ptr<sv::Plan>> plans;  // bounded: see kMaxPlans
+  uint64_t plan_clock = 0;
   sv::Plan* last_plan = nullptr;
   int64_t launches = 0;
   // optional per-kernel-class timing (CUDA events around every launch; bench.py's roofline pass)
@@ -542,6 +547,9 @@ int build(sv_evp* h, Plan* plan, void* ws, int n, int H, int W, bool with_flow, 
     max_conv_out = std::max(max_conv_out, M * g[s].C);
   }
   const int fch[5] = {2, 64, 128, c.embed_dims[2], c.embed_dims[3]};
+  // the flow cross-attention keys/values cover the stage's FULL token grid (no spatial reduction): [n*N, 2C] in `kvb`
+  if (with_flow)
+    for (int s = 2; s < 4; ++s) max_kv_c = std::max(max_kv_c, static_cast<size_t>(n) * g[s].N * g[s].C);
   if (with_flow)
     for (int i = 0; i < 4; ++i) max_col = std::max(max_col, static_cast<size_t>(n) * g[i].N * round_up((i == 0 ? 49 : 9) * fch[i], 8));
 
@@ -906,11 +914,20 @@ int sv_evp_forward(sv_evp_handle* h, const float* x, const float* seg, const flo
     if (it == h->plans.end() || it->second->ws != workspace) {
       std::unique_ptr<Plan> p(new Plan());
       p->n = n; p->H = H; p->W = W; p->with_flow = with_flow; p->ws = workspace;
-      size_t need = 0;
-      SV_TRY(build(h, p.get(), workspace, n, H, W, with_flow, &need));
-      if (need > workspace_bytes) return fail(SV_ERR_INVALID, "evp: workspace too small for plan");
+      SV_TRY(build(h, p.get(), workspace, n, H, W, with_flow, &p->need));
+      if (it == h->plans.end() && h->plans.size() >= kMaxPlans) {  // evict the least recently used plan (never the one just run)
+        auto victim = h->plans.end();
+        for (auto jt = h->plans.begin(); jt != h->plans.end(); ++jt)
+          if (victim == h->plans.end() || jt->second->last_use < victim->second->last_use) victim = jt;
+        if (victim->second.get() == h->last_plan) h->last_plan = nullptr;
+        h->plans.erase(victim);
+      }
+      if (it != h->plans.end() && it->second.get() == h->last_plan) h->last_plan = nullptr;
       it = h->plans.insert_or_assign(key, std::move(p)).first;
     }
+    // checked on EVERY call: a cached plan addresses `need` bytes behind `workspace`, whatever size the caller passes this time
+    if (it->second->need > workspace_bytes) return fail(SV_ERR_INVALID, "evp: workspace too small for plan");
+    it->second->last_use = ++h->plan_clock;
     const Plan& plan = *it->second;
     const size_t in_off = static_cast<size_t>(b0) * 3 * H * W;
     SV_TRY(run_plan(h, plan, x + in_off, seg + in_off, with_flow ? flow + static_cast<size_t>(b0) * 2 * H * W : nullptr,

@@ -412,17 +412,8 @@ GemmKernelFn kernel_for(const GemmParams& p) {
 }  // namespace
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  static std::mutex mu;
-  static std::vector<const void*> configured;
   GemmKernelFn fn = kernel_for(plan.p);
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (std::find(configured.begin(), configured.end(), reinterpret_cast<const void*>(fn)) == configured.end()) {
-      cudaError_t e = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kEpiSmemBytes + 1024);
-      if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(gemm): ") + cudaGetErrorString(e));
-      configured.push_back(reinterpret_cast<const void*>(fn));
-    }
-  }
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), kSmemBudget + kEpiSmemBytes + 1024));
   if (plan.p.pair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);

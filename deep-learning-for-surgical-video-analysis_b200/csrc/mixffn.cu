@@ -481,10 +481,7 @@ int mixffn_fc2_plan(const bf16* h1, const float* w10c, const bf16* Wcat, int64_t
 }
 
 int mixffn_fc2_launch(const MixffnPlan& plan, cudaStream_t st) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mixffn_fc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit + 1024); });
-  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(mixffn): ") + cudaGetErrorString(attr_err));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mixffn_fc2_kernel), kSmemLimit + 1024));
   const MixParams& p = *reinterpret_cast<const MixParams*>(plan.params);
   mixffn_fc2_kernel<<<plan.grid, kThreads, plan.smem_bytes, st>>>(plan.tmap_h1, plan.tmap_dw, plan.tmap_w, plan.tmap_t, p);
   return launch_status("mixffn_fc2_kernel");

@@ -347,7 +347,7 @@ int launch_inproj(sv_mstcn* h, const float* feats, int64_t T, float* out, float*
   const sv_mstcn::Stage& S = h->stages[0];
   const float* W = h->d_weights;
   constexpr size_t smem = (3 * 128 * (32 + 4) + 2 * 3 * 32 * (F + Q + 8)) * sizeof(float);
-  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_inproj_tf32x3_kernel<F, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mstcn_inproj_tf32x3_kernel<F, Q>), static_cast<int>(smem)));
   mstcn_inproj_tf32x3_kernel<F, Q><<<static_cast<unsigned>(ceil_div64(T, 128)), 128, smem, st>>>(feats, W + S.w_in_hi, W + S.w_in_lo, W + S.b_in, T,
                                                                                                  h->cfg.f_dim, out, query, h->q_out);
   return launch_status("mstcn_inproj_tf32x3_kernel");
@@ -369,7 +369,7 @@ int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n
   const size_t layer_smem = (3 * F * F + F * F + 2 * F) * sizeof(float);
   constexpr int NS = 1;  // time steps per thread in the layer kernel (NS = 2 measured slower on B200: 167 registers, 92 vs 76 us)
   const unsigned lb = static_cast<unsigned>(ceil_div64(ceil_div64(T, NS), 128));
-  SV_CUDA_OK(cudaFuncSetAttribute(mstcn_layer_kernel<F, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(layer_smem)));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mstcn_layer_kernel<F, NS>), static_cast<int>(layer_smem)));
   float* cur = bufA;  // current stage input / running activation
   float* nxt = bufB;
   for (int s = 0; s < c.stages; ++s) {

@@ -188,10 +188,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
 template <int COUT>
 int stem_launch(const StemParams& p, cudaStream_t st) {
   constexpr size_t smem = (static_cast<size_t>(COUT) * kLdA + 64 * kLdA + 3 * kPatch * (kPatch + 5)) * sizeof(bf16);
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(stem_conv_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); });
-  if (attr_err != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaFuncSetAttribute(stem): ") + cudaGetErrorString(attr_err));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(stem_conv_kernel<COUT>), static_cast<int>(smem)));
   const long long tiles = static_cast<long long>(p.B) * p.tiles_x * p.tiles_y;
   const int grid = static_cast<int>(std::min<long long>(tiles, 8LL * device_sm_count()));
   stem_conv_kernel<COUT><<<grid, 128, smem, st>>>(p);

@@ -185,8 +185,8 @@ class MultiStageModel_S(nn.Module):
                 if st.get("id") is not None:
                     ops.unregister_handle(st["id"])
                 _native.lib().sv_mstcn_destroy(st["handle"])
-        except Exception:
-            pass
+        except (AttributeError, TypeError, ImportError):
+            pass  # interpreter shutdown: module globals are already gone; anything else (a failing destroy) propagates as "ignored exception" text
 
 
 class _MstcnOpOwner:

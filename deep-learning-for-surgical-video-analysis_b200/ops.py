@@ -6,6 +6,7 @@ and the stream; all arithmetic happens inside libsurgvid.so.  CUDA only — ther
 from __future__ import annotations
 
 import ctypes
+import itertools
 from typing import Dict, Optional
 
 import torch
@@ -90,8 +91,12 @@ def causal_windows(x: torch.Tensor, lengths, len_q: int) -> torch.Tensor:
     return out
 
 
+_NEXT_HANDLE = itertools.count(1)
+
+
 def register_handle(owner) -> int:
-    hid = id(owner)
+    """A fresh integer id per registration (never reused, unlike id(owner) after garbage collection)."""
+    hid = next(_NEXT_HANDLE)
     _HANDLES[hid] = owner
     return hid
 

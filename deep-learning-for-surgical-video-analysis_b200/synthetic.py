@@ -284,3 +284,47 @@ def synth_mstcn_state_dict(stages=2, layers=8, f_maps=32, f_dim=2048, out_featur
         for c in range(7):
             sd[p + ".conv_out_classes.weight"][c, c, 0] += 1.5
     return sd
+
+
+# ----------------------------------------------------------------------------------------------- chained (encoder -> MS-TCN) gate
+def phase_schedule(T: int, seed: int) -> torch.Tensor:
+    """Piecewise-constant pseudo-phase id (0..6) per frame: a random order of the 7 phases with random boundaries, as in
+    `synth_lfb_features`."""
+    g = torch.Generator().manual_seed(3_000_000 + seed)
+    order = torch.randperm(7, generator=g)
+    bounds = torch.sort(torch.rand(6, generator=g)).values
+    t = (torch.arange(T, dtype=torch.float32) + 0.5) / max(T, 1)
+    return order[(t[:, None] > bounds[None, :]).sum(dim=1)]
+
+
+def synth_phase_frames(T: int, seed: int, H: int = 224, W: int = 224, amp: float = 1.0, phase: "torch.Tensor | None" = None):
+    """`synth_frames` plus a per-phase low-frequency image pattern added to the frames (7 fixed 7x7 random fields, bilinearly
+    upsampled), so that the ENCODER's features carry a phase signal and the chained LFB -> MS-TCN argmax is not a constant class.
+    Returns (x, seg, flow, phase)."""
+    x, seg, flow = synth_frames(T, seed, H, W)
+    if phase is None:
+        phase = phase_schedule(T, seed)
+    pat = torch.nn.functional.interpolate(torch.randn(7, 3, 7, 7, generator=torch.Generator().manual_seed(99)), size=(H, W), mode="bilinear",
+                                          align_corners=False)
+    return x + amp * pat[phase].unsqueeze(1), seg, flow, phase
+
+
+def synth_mstcn_state_dict_for_protos(dev_protos: torch.Tensor, center: torch.Tensor, gain: float = 3.0, stages=2, layers=8, f_maps=32, out_features=14,
+                                      seed: int = 1):
+    """MS-TCN "phase" weights whose class c (< 7) responds to feature deviation `dev_protos[c]` from `center` (both measured on a
+    calibration set of encoder features): stage-1 projection row c += gain * d_c / |d_c|^2, bias compensates the centre."""
+    f_dim = dev_protos.shape[1]
+    sd = synth_state_dict(mstcn_key_shapes(stages, layers, f_maps, f_dim, out_features), seed, "stress")
+    for k in sd:
+        if k.endswith("weight"):
+            sd[k] = sd[k] * 0.5
+    w = gain * dev_protos / (dev_protos.norm(dim=1, keepdim=True) ** 2)
+    sd["stage1_phase.conv_1x1.weight"][:7, :, 0] += w
+    sd["stage1_phase.conv_1x1.bias"][:7] -= w @ center
+    for p, gain_in in (("stage1_phase", None), ) + tuple((f"stages.{s}", 3.0) for s in range(stages - 1)):
+        if gain_in is not None:
+            for c in range(7):
+                sd[p + ".conv_1x1.weight"][c, c, 0] += gain_in
+        for c in range(7):
+            sd[p + ".conv_out_classes.weight"][c, c, 0] += 1.5
+    return sd
