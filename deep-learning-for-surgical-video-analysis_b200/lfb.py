@@ -157,8 +157,8 @@ class CyclicFrames:
 def _as_frames(t, trailing):
     """[N,(1,)C,H,W]-like tensor -> [N, *trailing] view; CyclicFrames pass through (their pool already has that layout)."""
     if isinstance(t, CyclicFrames):
-        if tuple(t.shape[1:]) != tuple(trailing):
-            raise ValueError("CyclicFrames pool has the wrong frame shape")
+        if tuple(t.shape[1:]) != tuple(trailing):   # e.g. a [P,1,3,H,W] pool (the reference's sequence_length-1 axis): view it as [P,3,H,W]
+            return CyclicFrames(t.pool.reshape((t.pool.shape[0],) + tuple(trailing)), t.start, t.length)
         return t
     return t.reshape((t.shape[0],) + tuple(trailing))
 
