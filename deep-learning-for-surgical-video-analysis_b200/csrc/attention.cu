@@ -563,6 +563,11 @@ int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, con
   SV_CHECK(B <= 65535 && heads <= 65535, "attention grid limits");
   SV_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 2 == 0, "attention leading dims must keep 16-byte row alignment");
   SV_CHECK(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0, "attention operand alignment");
+  if (attention_tc_enabled() && attention_tc_supported(hd, Nkv, ldq, ldk, ldv, ldo, q, k, v, o)) {
+    AttnTcPlan plan;
+    SV_TRY(attention_tc_plan(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, &plan));
+    return attention_tc_launch(plan, st);
+  }
   switch (hd) {
     case 20: return attn_launch<20>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);
     case 32: return attn_launch<32>(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, scale, st);

@@ -64,6 +64,8 @@ struct Op {
   GemmPlan gemm;
   DwconvPlan dw;
   bool dw_tma = false;
+  AttnTcPlan attn_tc;
+  bool attn_tc_on = false;
   // generic arguments (meaning depends on kind)
   const void* src = nullptr;
   const void* src2 = nullptr;
@@ -483,6 +485,10 @@ struct Builder {
     Op op; op.kind = OP_ATTN; op.src = q; op.src2 = k; op.src3 = v; op.dst = o; op.l0 = ldq; op.l1 = ldk; op.l2 = ldv; op.l3 = ldo;
     op.i[0] = B; op.i[1] = heads; op.i[2] = Nq; op.i[3] = Nkv; op.i[4] = hd; op.f0 = 1.0f / sqrtf(static_cast<float>(hd));
     op.alg_bytes = 2.0 * B * heads * hd * (2.0 * Nq + 2.0 * Nkv);
+    if (!dry() && status == SV_OK && attention_tc_enabled() && attention_tc_supported(hd, Nkv, ldq, ldk, ldv, ldo, q, k, v, o)) {
+      op.attn_tc_on = true;
+      status = attention_tc_plan(q, ldq, k, ldk, v, ldv, o, ldo, B, heads, Nq, Nkv, op.f0, &op.attn_tc);
+    }
     push(op);
   }
   void gauss(float* out, int planes, int H, int W) {
@@ -759,6 +765,7 @@ int run_plan(sv_evp* h, const Plan& p, const float* x, const float* seg, const f
         rc = launch_dwconv3x3_gelu(static_cast<const bf16*>(op.src), op.p0, op.p1, op.i[0], op.i[1], op.i[2], op.i[3], static_cast<bf16*>(op.dst), op.l0, st);
         break;
       case OP_ATTN:
+        if (op.attn_tc_on) { rc = attention_tc_launch(op.attn_tc, st); break; }
         rc = launch_attention(static_cast<const bf16*>(op.src), op.l0, static_cast<const bf16*>(op.src2), op.l1, static_cast<const bf16*>(op.src3),
                               op.l2, static_cast<bf16*>(op.dst), op.l3, op.i[0], op.i[1], op.i[2], op.i[3], op.i[4], op.f0, st);
         break;

@@ -19,6 +19,19 @@ int launch_bf16_to_f32(const bf16* x, float* out, int64_t n, cudaStream_t st);
 int launch_attention(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B,
                      int heads, int Nq, int Nkv, int hd, float scale, cudaStream_t st);
 
+// tcgen05/TMEM attention for head_dim 64, N_kv <= 448 (attention_tc.cu); the plan owns the four 3-D tensor maps
+struct AttnTcPlan {
+  CUtensorMap tmap_q, tmap_k, tmap_v, tmap_o;
+  int B = 0, heads = 0, Nq = 0, Nkv = 0, kt = 0, qtiles = 0, tpc = 1, tmem_cols = 0;
+  float scale_log2 = 0.f;
+  size_t smem_bytes = 0;
+};
+bool attention_tc_enabled();   // SURGVID_ATTN_TC=0 selects the mma.sync kernels everywhere (A/B switch)
+bool attention_tc_supported(int hd, int Nkv, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k, const void* v, const void* o);
+int attention_tc_plan(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, const bf16* v, int64_t ldv, bf16* o, int64_t ldo, int B, int heads,
+                      int Nq, int Nkv, float scale, AttnTcPlan* plan);
+int attention_tc_launch(const AttnTcPlan& plan, cudaStream_t st);
+
 // TMA-staged persistent depthwise conv (dwconv_tma.cu); the plan owns the tensor map of the input
 struct DwconvPlan {
   CUtensorMap tmap;

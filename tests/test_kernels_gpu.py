@@ -139,7 +139,10 @@ def test_dwconv3x3_gelu(shape):
 
 @pytest.mark.parametrize("cfg", [(3, 1, 3136, 49, 64), (2, 2, 784, 49, 64), (2, 5, 196, 49, 64), (3, 8, 49, 49, 64), (2, 8, 196, 196, 40),
                                  (1, 1, 1000, 390, 64), (2, 8, 405, 405, 64), (2, 5, 160, 70, 32), (1, 2, 5, 3, 64),
-                                 (2, 8, 196, 196, 20), (3, 8, 49, 49, 20), (1, 8, 300, 330, 20)])   # head_dim 20: mit_b0_evp flow cross-attention
+                                 (2, 8, 196, 196, 20), (3, 8, 49, 49, 20), (1, 8, 300, 330, 20),   # head_dim 20: mit_b0_evp flow cross-attention
+                                 # tcgen05 path (head_dim 64, N_kv <= 448): several query tiles per CTA, exact / ragged tile edges, 1..7 key tiles
+                                 (40, 1, 3136, 49, 64), (3, 2, 128, 64, 64), (3, 2, 129, 65, 64), (2, 3, 300, 128, 64), (2, 2, 257, 448, 64),
+                                 (1, 2, 700, 200, 64), (2, 1, 1620, 405, 64), (1, 2, 64, 449, 64)])
 def test_attention(cfg):
     B, heads, Nq, Nkv, hd = cfg
     C = heads * hd
