@@ -2,15 +2,22 @@
 // every encoder block of mit_b1..b5_evp (mix_transformer_evp.py:123-127; N_kv = 49 at 224x224, 390/405 at 480x854).
 //
 // One CTA = one (frame, head) and a run of 128-row query tiles; K and V of the (frame, head) stay resident in shared memory.
-//   warp 4   TMA: K/V tiles once, Q tiles double-buffered (3-D tensor maps [C, N, frames]: rows past the frame's last token are
-//            zero-filled on load and clipped on store, so tiles never bleed into the next frame); O tiles back with a TMA store.
-//   warp 5   one thread issues tcgen05.mma: S = Q K^T (M=128, N=64 per key tile, K = 64) into TMEM columns [0, 64*kt), then
-//            O += P_t V_t per key tile (A = P from shared memory, B = V as an MN-major operand: V is used as stored, no transpose).
-//   warps 0-3  softmax: thread = query row (TMEM lane).  tcgen05.ld of the S row, scale in the log2 domain, mask keys >= N_kv,
-//            row max, exp2, row sum; P as bf16 into the 128B-swizzled K-major A tile (generic-proxy stores + fence.proxy.async);
-//            after the PV MMAs: O row from TMEM, * 1/l, bf16, into the (consumed) Q buffer in the swizzled layout of the TMA store.
-// With several key tiles (480x854) all of S (up to 448 columns) sits in TMEM at once: exact two-pass softmax, no online rescaling
-// of O; the P tiles go through a 2-deep ring so the PV MMA of tile t overlaps the exponentials of tile t+1.
+//   warp 8     TMA loads: K/V tiles once, Q tiles through a 2-deep ring that is refilled as soon as the S MMAs of a tile have read it
+//              (3-D tensor maps [C, N, frames]: rows past the frame's last token are zero-filled on load and clipped on store, so
+//              tiles never bleed into the next frame).
+//   warp 10    TMA stores of the finished output tiles (staged in the P buffer the tile's PV MMAs have consumed).
+//   warp 9     one thread issues tcgen05.mma: S = Q K^T (M=128, N=64 per key tile, K = 64) into TMEM, then O += P_t V_t per key tile
+//              (A = P from shared memory, B = V as an MN-major operand: V is used as stored, no transpose).
+//   warps 0-7  two softmax groups of 4 warps; thread = query row (TMEM lane).  tcgen05.ld of the S row, scale in the log2 domain, mask
+//              keys >= N_kv, row max, exp2, row sum; P as bf16 into the 128B-swizzled K-major A tile (generic-proxy stores +
+//              fence.proxy.async); after the PV MMAs: O row from TMEM, * 1/l, bf16, into the (consumed) P buffer in the swizzled
+//              layout of the TMA store.
+// N_kv <= 64 (one key tile; 224x224): the groups PING-PONG over query tiles — S and O are double-buffered in TMEM (256 columns), so
+// the MMAs and TMEM round trips of one tile hide behind the exponentials of the other.
+// 64 < N_kv <= 448 (480x854): all of S (up to 448 columns) sits in TMEM at once — exact two-pass softmax, no online rescaling of O.
+// Both groups work on the SAME query tile: group g takes the key tiles t = g (mod 2) and owns P buffer g of the 2-deep ring (the PV
+// MMA of tile t overlaps the exponentials of tile t+1); row max and row sum are exchanged through shared memory; each group
+// normalises and stages one half of the output columns.
 #include <stdlib.h>
 
 #include <mutex>
@@ -28,7 +35,7 @@ constexpr int kKeys = 64;               // keys per tile == UMMA N of S == K ext
 constexpr int kMaxKt = 7;               // 7 * 64 S columns + 64 O columns = 512 TMEM columns
 constexpr int kQBytes = kQRows * kHD * 2;   // 16 KB
 constexpr int kKBytes = kKeys * kHD * 2;    // 8 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 384;               // 8 softmax warps + a control warpgroup: Q/K/V loader, MMA issuer, output store (+ 1 idle)
 
 struct AttnTcParams {
   int Nq, Nkv, kt, tpc, qtiles;
@@ -63,13 +70,48 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) 
   return d;
 }
 
-// one 64-element bf16 row (8 chunks of 16 B) of a 128B-swizzled tile: chunk c of row r lives at r*128 + ((c ^ (r & 7)) << 4)
-__device__ __forceinline__ void store_row_sw128(uint8_t* tile, int row, const uint32_t (&w)[32]) {
+// chunks [c_begin, c_begin + 4) (32 bf16) of row `row` of a 128B-swizzled tile: chunk c lives at row*128 + ((c ^ (row & 7)) << 4)
+__device__ __forceinline__ void store_half_row_sw128(uint8_t* tile, int row, int c_begin, const uint32_t (&w)[16]) {
   uint8_t* rp = tile + row * 128;
   const int x = row & 7;
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<uint4*>(rp + ((c ^ x) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<uint4*>(rp + (((c_begin + c) ^ x) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// max over the valid keys of 32 raw scores (key index kbase + i)
+__device__ __forceinline__ float max32(const uint32_t (&r)[32], int kbase, int Nkv, float m) {
+  if (kbase + 32 <= Nkv) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, (kbase + i < Nkv) ? __uint_as_float(r[i]) : -INFINITY);
+  }
+  return m;
+}
+// p = exp2(s * scale - m) for 32 scores -> 16 packed bf16x2 words; returns the partial row sum
+__device__ __forceinline__ float exp32(const uint32_t (&r)[32], int kbase, int Nkv, float scale_log2, float m, uint32_t (&w)[16]) {
+  float l0 = 0.f, l1 = 0.f;
+  if (kbase + 32 <= Nkv) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float a0 = sv_ex2(fmaf(__uint_as_float(r[i]), scale_log2, -m));       // arguments <= 0: ex2.approx.ftz, 2 ulp
+      const float a1 = sv_ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m));
+      l0 += a0; l1 += a1;
+      w[i >> 1] = pack_bf16x2(a0, a1);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float a0 = (kbase + i < Nkv) ? sv_ex2(fmaf(__uint_as_float(r[i]), scale_log2, -m)) : 0.f;
+      const float a1 = (kbase + i + 1 < Nkv) ? sv_ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m)) : 0.f;
+      l0 += a0; l1 += a1;
+      w[i >> 1] = pack_bf16x2(a0, a1);
+    }
+  }
+  return l0 + l1;
 }
 
 template <bool MULTI>
@@ -77,7 +119,8 @@ __global__ void __launch_bounds__(kThreads, MULTI ? 1 : 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                     const __grid_constant__ CUtensorMap tmap_o, const AttnTcParams p) {
   extern __shared__ uint8_t attn_tc_smem[];
-  __shared__ __align__(8) uint64_t kv_full, q_full[2], s_full, p_full[2], p_empty[2], o_full, o_staged;
+  __shared__ __align__(8) uint64_t kv_full, q_full[2], q_empty[2], s_full[2], p_full[2], p_empty[2], o_full[2], o_staged[2], st_done[2];
+  __shared__ float xch[2][2][kQRows];   // MULTI: [row max | row sum][group][row]
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,29 +129,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const int ntiles = min(p.tpc, p.qtiles - tile0);
   const int kt = MULTI ? p.kt : 1;
   uint8_t* smem = attn_tc_smem + ((1024u - (ptx::smem_u32(attn_tc_smem) & 1023u)) & 1023u);
-  uint8_t* Qs = smem;                       // [2][16 KB]; tile j's buffer doubles as the staging tile of its output
+  uint8_t* Qs = smem;                       // [2][16 KB]
   uint8_t* Ks = Qs + 2 * kQBytes;           // [kt][8 KB]
   uint8_t* Vs = Ks + kt * kKBytes;          // [kt][8 KB]
-  uint8_t* Ps = Vs + kt * kKBytes;          // [MULTI ? 2 : 1][16 KB]
+  uint8_t* Ps = Vs + kt * kKBytes;          // [2][16 KB]; a consumed P buffer doubles as the staging tile of the output
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_q);
     ptx::prefetch_tensormap(&tmap_k);
     ptx::prefetch_tensormap(&tmap_v);
     ptx::prefetch_tensormap(&tmap_o);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     if (lane == 0) {
       ptx::mbar_init(&kv_full, 1);
-      ptx::mbar_init(&q_full[0], 1);
-      ptx::mbar_init(&q_full[1], 1);
-      ptx::mbar_init(&s_full, 1);
-      ptx::mbar_init(&p_full[0], 128);
-      ptx::mbar_init(&p_full[1], 128);
-      ptx::mbar_init(&p_empty[0], 1);
-      ptx::mbar_init(&p_empty[1], 1);
-      ptx::mbar_init(&o_full, 1);
-      ptx::mbar_init(&o_staged, 128);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&q_full[i], 1);
+        ptx::mbar_init(&q_empty[i], 1);
+        ptx::mbar_init(&st_done[i], 1);
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&p_full[i], 128);
+        ptx::mbar_init(&p_empty[i], 1);
+        ptx::mbar_init(&o_full[i], 1);
+        ptx::mbar_init(&o_staged[i], MULTI ? 256 : 128);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -119,161 +163,232 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_o = tmem_base + static_cast<uint32_t>(kt * kKeys);
+  // TMEM columns.  one key tile: S of group g at 64g, O of group g at 128 + 64g.  several: S tile t at 64t, O at 64*kt.
+  const uint32_t tmem_o = tmem_base + static_cast<uint32_t>(MULTI ? kt * kKeys : 2 * kKeys);
   const int c0 = head * kHD;
 
-  if (warp == 4) {
-    // ------------------------------------------------------------------ TMA: loads, and the stores of finished output tiles
+  // register budget: the control warpgroup gives registers back, the two softmax warpgroups take them.  setmaxnreg moves registers
+  // inside the CTA's LAUNCH allocation only (384 threads x 80 at one key tile): 8 * 96 + 4 * 48 = 12 * 80.
+  if (warp >= 8) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");   // one instruction for the whole control warpgroup (warps 8-11)
+  if (warp == 8) {
+    // ------------------------------------------------------------------ TMA loads
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(&kv_full, static_cast<uint32_t>(2 * kt * kKBytes));
       for (int t = 0; t < kt; ++t) {
         tma_load_3d(Ks + t * kKBytes, &tmap_k, &kv_full, c0, t * kKeys, b);
         tma_load_3d(Vs + t * kKBytes, &tmap_v, &kv_full, c0, t * kKeys, b);
       }
-      for (int j = 0; j < 2 && j < ntiles; ++j) {
-        ptx::mbar_arrive_expect_tx(&q_full[j], kQBytes);
-        tma_load_3d(Qs + j * kQBytes, &tmap_q, &q_full[j], c0, (tile0 + j) * kQRows, b);
-      }
       for (int j = 0; j < ntiles; ++j) {
-        ptx::mbar_wait(&o_staged, static_cast<uint32_t>(j & 1));   // the 128 rows of O_j are staged in Q buffer j&1 (and fenced)
-        tma_store_3d(&tmap_o, Qs + (j & 1) * kQBytes, c0, (tile0 + j) * kQRows, b);
-        tma_store_commit();
-        tma_store_wait_read();                                     // the store has read the buffer: it may be refilled / the CTA may exit
-        if (j + 2 < ntiles) {
-          ptx::mbar_arrive_expect_tx(&q_full[j & 1], kQBytes);
-          tma_load_3d(Qs + (j & 1) * kQBytes, &tmap_q, &q_full[j & 1], c0, (tile0 + j + 2) * kQRows, b);
-        }
+        const int qb = j & 1;
+        if (j >= 2) ptx::mbar_wait(&q_empty[qb], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // the S MMAs of tile j-2 have read this buffer
+        ptx::mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+        tma_load_3d(Qs + qb * kQBytes, &tmap_q, &q_full[qb], c0, (tile0 + j) * kQRows, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 10) {
+    // ------------------------------------------------------------------ TMA stores of the output tiles (warp 11 idles)
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int sb = MULTI ? 0 : (j & 1);
+        ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((MULTI ? j : (j >> 1)) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+        tma_store_3d(&tmap_o, Ps + sb * kQBytes, c0, (tile0 + j) * kQRows, b);
+        tma_store_commit();
+        tma_store_wait_read();                  // the store has read the buffer: P may be overwritten / the CTA may exit
+        ptx::mbar_arrive(&st_done[sb]);
+      }
+    }
+  } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t idesc_s = ptx::make_idesc_bf16_f32(kQRows, kKeys);                 // A, B K-major
       const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(kQRows, kHD) | (1u << 16);     // B (= V) MN-major
-      uint32_t ph_q[2] = {0u, 0u};
-      uint32_t n_pf[2] = {0u, 0u};
       ptx::mbar_wait(&kv_full, 0u);
-      for (int j = 0; j < ntiles; ++j) {
-        const int qb = j & 1;
-        ptx::mbar_wait(&q_full[qb], ph_q[qb]);
-        ph_q[qb] ^= 1u;
-        ptx::tc_fence_after();
-        const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + qb * kQBytes));
-        for (int t = 0; t < kt; ++t) {
-          const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + t * kKBytes));
+      if (!MULTI) {
+        // issue order S_0, S_1, PV_0, S_2, PV_1, ...: the S MMA of the next tile is in flight while a group does its exponentials
+        const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks));
+        const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs));
+        for (int j = 0; j <= ntiles; ++j) {
+          if (j < ntiles) {
+            const int g = j & 1;
+            ptx::mbar_wait(&q_full[g], static_cast<uint32_t>((j >> 1) & 1));
+            ptx::tc_fence_after();
+            const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + g * kQBytes));
 #pragma unroll
-          for (int ks = 0; ks < kHD / 16; ++ks)
-            ptx::umma_f16(tmem_base + static_cast<uint32_t>(t * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+            for (int ks = 0; ks < kHD / 16; ++ks)
+              ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+            ptx::umma_commit(&s_full[g]);
+            ptx::umma_commit(&q_empty[g]);
+          }
+          if (j >= 1) {
+            const int jj = j - 1, g = jj & 1;
+            // P_jj is in shared memory; the same arrivals order the group's reads of S_jj and of O_{jj-2} before this point
+            ptx::mbar_wait(&p_full[g], static_cast<uint32_t>((jj >> 1) & 1));
+            ptx::tc_fence_after();
+            const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + g * kQBytes));
+#pragma unroll
+            for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
+              ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
+                            ks ? 1u : 0u);
+            ptx::umma_commit(&o_full[g]);
+          }
         }
-        ptx::umma_commit(&s_full);
-        for (int t = 0; t < kt; ++t) {
-          const int pb = t & 1;
-          ptx::mbar_wait(&p_full[pb], n_pf[pb] & 1u);
-          ++n_pf[pb];
-          if (t == 0 && j > 0) ptx::mbar_wait(&o_staged, static_cast<uint32_t>((j - 1) & 1));   // O_{j-1} has left TMEM
+      } else {
+        uint32_t n_pf[2] = {0u, 0u};
+        for (int j = 0; j < ntiles; ++j) {
+          const int qb = j & 1;
+          ptx::mbar_wait(&q_full[qb], static_cast<uint32_t>((j >> 1) & 1));
           ptx::tc_fence_after();
-          const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + pb * kQBytes));
-          const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs + t * kKBytes));
+          const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + qb * kQBytes));
+          for (int t = 0; t < kt; ++t) {
+            const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + t * kKBytes));
 #pragma unroll
-          for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
-            ptx::umma_f16(tmem_o, dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv, (t | ks) ? 1u : 0u);
-          ptx::umma_commit(&p_empty[pb]);
+            for (int ks = 0; ks < kHD / 16; ++ks)
+              ptx::umma_f16(tmem_base + static_cast<uint32_t>(t * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+          }
+          ptx::umma_commit(&s_full[0]);
+          ptx::umma_commit(&q_empty[qb]);
+          for (int t = 0; t < kt; ++t) {
+            const int pb = t & 1;
+            const uint32_t par = (pb ? n_pf[1] : n_pf[0]) & 1u;
+            ptx::mbar_wait(&p_full[pb], par);
+            if (pb) ++n_pf[1]; else ++n_pf[0];
+            if (t == 0 && j > 0) ptx::mbar_wait(&o_staged[0], static_cast<uint32_t>((j - 1) & 1));   // O_{j-1} has left TMEM
+            ptx::tc_fence_after();
+            const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + pb * kQBytes));
+            const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs + t * kKBytes));
+#pragma unroll
+            for (int ks = 0; ks < kKeys / 16; ++ks)
+              ptx::umma_f16(tmem_o, dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv, (t | ks) ? 1u : 0u);
+            ptx::umma_commit(&p_empty[pb]);
+          }
+          ptx::umma_commit(&o_full[0]);
         }
-        ptx::umma_commit(&o_full);
       }
     }
+  }
   } else {
     // ------------------------------------------------------------------ softmax + output rows (thread = query row = TMEM lane)
-    const int row = warp * 32 + lane;
-    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const uint32_t t_o = tmem_o + (static_cast<uint32_t>(warp * 32) << 16);
-    uint32_t ph_s = 0u, ph_o = 0u;
-    uint32_t n_pe[2] = {0u, 0u};
-    for (int j = 0; j < ntiles; ++j) {
-      const bool active = (tile0 + j) * kQRows + warp * 32 < p.Nq;   // warp-uniform: rows past the frame's last query do no math
-      ptx::mbar_wait(&s_full, ph_s);
-      ph_s ^= 1u;
-      ptx::tc_fence_after();
-      float m = -INFINITY, l = 0.f;
-      if (MULTI && active) {
-        for (int t = 0; t < kt; ++t) {
-          uint32_t r[32];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ptx::tmem_ld_x32(t_s + static_cast<uint32_t>(t * kKeys + h * 32), r);
-            ptx::tmem_ld_wait();
-            const int kbase = t * kKeys + h * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float s = __uint_as_float(r[i]);
-              m = fmaxf(m, (kbase + i < p.Nkv) ? s : -INFINITY);
-            }
-          }
-        }
-        m *= p.scale_log2;   // scale > 0: max commutes with it
-      }
-      for (int t = 0; t < kt; ++t) {
-        const int pb = t & 1;
-        uint8_t* Pt = Ps + pb * kQBytes;
-        if (n_pe[pb] > 0u) ptx::mbar_wait(&p_empty[pb], (n_pe[pb] - 1u) & 1u);   // the PV MMA that read this P buffer last has retired
-        ++n_pe[pb];
+    if (MULTI) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    if (!MULTI) {
+      const uint32_t t_s = tmem_base + static_cast<uint32_t>(grp * kKeys) + lane_sel;
+      const uint32_t t_o = tmem_o + static_cast<uint32_t>(grp * kHD) + lane_sel;
+      uint8_t* Pg = Ps + grp * kQBytes;
+      for (int j = grp; j < ntiles; j += 2) {
+        const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
+        const bool active = (tile0 + j) * kQRows + quarter * 32 < p.Nq;   // warp-uniform: rows past the frame's last query do no math
+        ptx::mbar_wait(&s_full[grp], par);
+        ptx::tc_fence_after();
+        float l = 1.f;
         if (active) {
           uint32_t r0[32], r1[32];
-          ptx::tmem_ld_x32(t_s + static_cast<uint32_t>(t * kKeys), r0);
-          ptx::tmem_ld_x32(t_s + static_cast<uint32_t>(t * kKeys + 32), r1);
+          ptx::tmem_ld_x32(t_s, r0);
+          ptx::tmem_ld_x32(t_s + 32u, r1);
           ptx::tmem_ld_wait();
-          const int kbase = t * kKeys;
-          if (!MULTI) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              m = fmaxf(m, (i < p.Nkv) ? __uint_as_float(r0[i]) : -INFINITY);
-              m = fmaxf(m, (32 + i < p.Nkv) ? __uint_as_float(r1[i]) : -INFINITY);
-            }
-            m *= p.scale_log2;
-          }
-          uint32_t w[32];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float a0 = (kbase + i < p.Nkv) ? exp2f(fmaf(__uint_as_float(r0[i]), p.scale_log2, -m)) : 0.f;
-            const float a1 = (kbase + i + 1 < p.Nkv) ? exp2f(fmaf(__uint_as_float(r0[i + 1]), p.scale_log2, -m)) : 0.f;
-            const float b0 = (kbase + 32 + i < p.Nkv) ? exp2f(fmaf(__uint_as_float(r1[i]), p.scale_log2, -m)) : 0.f;
-            const float b1 = (kbase + 32 + i + 1 < p.Nkv) ? exp2f(fmaf(__uint_as_float(r1[i + 1]), p.scale_log2, -m)) : 0.f;
-            l += (a0 + a1) + (b0 + b1);
-            w[i >> 1] = pack_bf16x2(a0, a1);
-            w[16 + (i >> 1)] = pack_bf16x2(b0, b1);
-          }
-          store_row_sw128(Pt, row, w);
+          float m = max32(r0, 0, p.Nkv, -INFINITY);
+          m = max32(r1, 32, p.Nkv, m) * p.scale_log2;   // scale > 0: max commutes with it
+          uint32_t w[16];
+          l = exp32(r0, 0, p.Nkv, p.scale_log2, m, w);
+          // P buffer `grp` is free: the PV MMAs of this group's previous tile retired before its o_full, and the TMA store of that
+          // tile's output (staged in the same buffer) has finished reading it
+          if (j >= 2) ptx::mbar_wait(&st_done[grp], static_cast<uint32_t>(((j - 2) >> 1) & 1));
+          store_half_row_sw128(Pg, row, 0, w);
+          l += exp32(r1, 32, p.Nkv, p.scale_log2, m, w);
+          store_half_row_sw128(Pg, row, 4, w);
         }
         ptx::fence_proxy_async_smem();   // generic-proxy stores of P -> visible to the tensor core
-        ptx::tc_fence_before();          // this thread's TMEM reads of S are complete (S may be overwritten once every row arrived)
-        ptx::mbar_arrive(&p_full[pb]);
-      }
-      ptx::mbar_wait(&o_full, ph_o);
-      ph_o ^= 1u;
-      ptx::tc_fence_after();
-      if (active) {
-        uint32_t r0[32], r1[32];
-        ptx::tmem_ld_x32(t_o, r0);
-        ptx::tmem_ld_x32(t_o + 32u, r1);
-        ptx::tmem_ld_wait();
-        const float inv = 1.0f / l;
-        uint32_t w[32];
+        ptx::tc_fence_before();          // this thread's TMEM reads of S are complete
+        ptx::mbar_arrive(&p_full[grp]);
+        ptx::mbar_wait(&o_full[grp], par);
+        ptx::tc_fence_after();
+        if (active) {
+          uint32_t r0[32], r1[32];
+          ptx::tmem_ld_x32(t_o, r0);
+          ptx::tmem_ld_x32(t_o + 32u, r1);
+          ptx::tmem_ld_wait();
+          const float inv = 1.0f / l;
+          uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          w[i >> 1] = pack_bf16x2(__uint_as_float(r0[i]) * inv, __uint_as_float(r0[i + 1]) * inv);
-          w[16 + (i >> 1)] = pack_bf16x2(__uint_as_float(r1[i]) * inv, __uint_as_float(r1[i + 1]) * inv);
+          for (int i = 0; i < 32; i += 2) w[i >> 1] = pack_bf16x2(__uint_as_float(r0[i]) * inv, __uint_as_float(r0[i + 1]) * inv);
+          store_half_row_sw128(Pg, row, 0, w);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) w[i >> 1] = pack_bf16x2(__uint_as_float(r1[i]) * inv, __uint_as_float(r1[i + 1]) * inv);
+          store_half_row_sw128(Pg, row, 4, w);
         }
-        store_row_sw128(Qs + (j & 1) * kQBytes, row, w);
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&o_staged[grp]);
       }
-      ptx::fence_proxy_async_smem();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&o_staged);
+    } else {
+      const uint32_t t_s = tmem_base + lane_sel;
+      const uint32_t t_o = tmem_o + static_cast<uint32_t>(grp * 32) + lane_sel;
+      uint8_t* Pg = Ps + grp * kQBytes;
+      uint32_t n_pe = 0u;
+      for (int j = 0; j < ntiles; ++j) {
+        const bool active = (tile0 + j) * kQRows + quarter * 32 < p.Nq;
+        ptx::mbar_wait(&s_full[0], static_cast<uint32_t>(j & 1));
+        ptx::tc_fence_after();
+        float m = -INFINITY;
+        if (active) {
+          for (int t = grp; t < kt; t += 2) {
+            uint32_t r[32];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              ptx::tmem_ld_x32(t_s + static_cast<uint32_t>(t * kKeys + h * 32), r);
+              ptx::tmem_ld_wait();
+              m = max32(r, t * kKeys + h * 32, p.Nkv, m);
+            }
+          }
+        }
+        xch[0][grp][row] = m;
+        named_bar_sync(1, 256);
+        m = fmaxf(xch[0][0][row], xch[0][1][row]) * p.scale_log2;   // finite for active rows: key 0 is valid and belongs to group 0
+        float l = 0.f;
+        for (int t = grp; t < kt; t += 2) {
+          if (n_pe > 0u) ptx::mbar_wait(&p_empty[grp], (n_pe - 1u) & 1u);   // the PV MMA that read this group's P buffer last has retired
+          ++n_pe;
+          if (grp == 0 && t == 0 && j > 0) ptx::mbar_wait(&st_done[0], static_cast<uint32_t>((j - 1) & 1));   // ... and the store of O_{j-1}, staged in P[0]
+          if (active) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              uint32_t r[32], w[16];
+              ptx::tmem_ld_x32(t_s + static_cast<uint32_t>(t * kKeys + h * 32), r);
+              ptx::tmem_ld_wait();
+              l += exp32(r, t * kKeys + h * 32, p.Nkv, p.scale_log2, m, w);
+              store_half_row_sw128(Pg, row, 4 * h, w);
+            }
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&p_full[grp]);
+        }
+        xch[1][grp][row] = l;
+        ptx::mbar_wait(&o_full[0], static_cast<uint32_t>(j & 1));
+        ptx::tc_fence_after();
+        named_bar_sync(2, 256);
+        if (active) {
+          const float inv = 1.0f / (xch[1][0][row] + xch[1][1][row]);
+          uint32_t r[32], w[16];
+          ptx::tmem_ld_x32(t_o, r);        // this group's half of the output columns
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) w[i >> 1] = pack_bf16x2(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+          store_half_row_sw128(Ps, row, 4 * grp, w);     // P[0]: every PV MMA of the tile has retired (o_full)
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&o_staged[0]);
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -340,10 +455,11 @@ int attention_tc_plan(const bf16* q, int64_t ldq, const bf16* k, int64_t ldk, co
   int tpc = 1;
   const long long want = 8LL * std::max(1, device_sm_count());
   while (tpc < 8 && tpc * 2 <= plan->qtiles && static_cast<long long>(ceil_div(plan->qtiles, tpc * 2)) * heads * B >= want) tpc *= 2;
+  if (plan->kt == 1 && tpc == 1 && plan->qtiles >= 2) tpc = 2;   // the two softmax groups ping-pong over a CTA's tiles
   plan->tpc = tpc;
-  const int need_cols = plan->kt * kKeys + kHD;
-  plan->tmem_cols = need_cols <= 128 ? 128 : (need_cols <= 256 ? 256 : 512);
-  plan->smem_bytes = 2 * kQBytes + 2 * plan->kt * kKBytes + (plan->kt > 1 ? 2 : 1) * kQBytes + 1024;
+  const int need_cols = plan->kt > 1 ? plan->kt * kKeys + kHD : 4 * kKeys;   // one key tile: S and O double-buffered (ping-pong groups)
+  plan->tmem_cols = need_cols <= 256 ? 256 : 512;
+  plan->smem_bytes = 2 * kQBytes + 2 * plan->kt * kKBytes + 2 * kQBytes + 1024;
   return SV_OK;
 }
 
@@ -356,7 +472,7 @@ int attention_tc_launch(const AttnTcPlan& plan, cudaStream_t st) {
     SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<true>), 2 * kQBytes + 2 * kMaxKt * kKBytes + 2 * kQBytes + 1024));
     attention_tc_kernel<true><<<grid, kThreads, plan.smem_bytes, st>>>(plan.tmap_q, plan.tmap_k, plan.tmap_v, plan.tmap_o, p);
   } else {
-    SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<false>), 3 * kQBytes + 2 * kKBytes + 1024));
+    SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<false>), 4 * kQBytes + 2 * kKBytes + 1024));
     attention_tc_kernel<false><<<grid, kThreads, plan.smem_bytes, st>>>(plan.tmap_q, plan.tmap_k, plan.tmap_v, plan.tmap_o, p);
   }
   return launch_status("attention_tc_kernel");

@@ -166,6 +166,48 @@ __device__ __forceinline__ void f2_gelu_erf_poly_x4(f32x2& xa, f32x2& xb, f32x2&
 #undef SV_C2
 }
 
+// GELU(erf) through the MUFU pipe, two lanes:  y = x * sigmoid(2 g(x)),  g(x) = x (c0 + c1 x^2 + c2 x^4) ~= atanh(erf(x / sqrt2))
+// (least-squares fit of the GELU itself on [-6, 6]: |GELU error| <= 3.0e-5 absolute, |erf error| <= 1.2e-4; x^2 is clamped at 49 where
+// the sigmoid has long saturated).  sigmoid = 1 / (1 + 2^t) with t = x * q(x^2), q = -2 log2(e) (c0 + c1 u + c2 u^2): one MUFU.EX2 and one
+// MUFU.RCP per element (relative error ~1e-6 each) and 6 FMA-pipe instructions per PAIR, against 13 for the MUFU-free polynomial —
+// the depthwise-conv kernel is bound by the FMA pipe, and the MUFU pipe is otherwise idle there.
+__device__ __forceinline__ float sv_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sv_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sv_tanh(float x) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+#define SV_GELU_G0 0.7974584707822386f
+#define SV_GELU_G1 0.03705034510045914f
+#define SV_GELU_G2 (-0.0003587323611556633f)
+__device__ __forceinline__ f32x2 f2_gelu_sigmoid(f32x2 x) {
+  const float k = -2.8853900817779268f;   // -2 log2(e)
+  f32x2 u = f2_mul(x, x);
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  u = f2_pack(fminf(u0, 49.f), fminf(u1, 49.f));
+  f32x2 q = f2_fma(u, f2_pack(k * SV_GELU_G2, k * SV_GELU_G2), f2_pack(k * SV_GELU_G1, k * SV_GELU_G1));
+  q = f2_fma(q, u, f2_pack(k * SV_GELU_G0, k * SV_GELU_G0));
+  float t0, t1;
+  f2_unpack(f2_mul(x, q), t0, t1);
+  const f32x2 d = f2_add(f2_pack(sv_ex2(t0), sv_ex2(t1)), f2_pack(1.f, 1.f));
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  return f2_mul(x, f2_pack(sv_rcp(d0), sv_rcp(d1)));
+}
+// same g(x), but y = 0.5 x (1 + tanh(g)): ONE MUFU per element; tanh.approx carries ~2^-11 relative error, i.e. up to ~2.5e-4 |x|
+// absolute on the result (worst in the negative tail, where 1 + tanh cancels)
+__device__ __forceinline__ f32x2 f2_gelu_tanh(f32x2 x) {
+  f32x2 u = f2_mul(x, x);
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  u = f2_pack(fminf(u0, 49.f), fminf(u1, 49.f));
+  f32x2 q = f2_fma(u, f2_pack(SV_GELU_G2, SV_GELU_G2), f2_pack(SV_GELU_G1, SV_GELU_G1));
+  q = f2_fma(q, u, f2_pack(SV_GELU_G0, SV_GELU_G0));
+  float t0, t1;
+  f2_unpack(f2_mul(x, q), t0, t1);
+  const f32x2 hx = f2_mul(x, f2_pack(0.5f, 0.5f));
+  return f2_fma(hx, f2_pack(sv_tanh(t0), sv_tanh(t1)), hx);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -5,7 +5,10 @@
 // video boundaries, so one launch per layer covers every video.  The causal branch (mstcn_causal_conv=True) is
 //   y[t] = x[t] + W1 * relu(Wd[0] x[t-2d] + Wd[1] x[t-d] + Wd[2] x[t] + bd) + b1        (mstcn.py:208-214)
 // which equals conv(pad 2d) -> relu -> drop last 2d samples -> 1x1 -> add.
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include <map>
 #include <string>
@@ -232,6 +235,138 @@ __global__ void __launch_bounds__(128) mstcn_layer_kernel(const float* __restric
   }
 }
 
+// ---- one DilatedResidualLayer on tensor cores, F = 32 (the path's f_maps): both convolutions of the layer are small GEMMs over time
+// rows — the dilated conv is [rows, 3F] x [3F, F] (the three taps are three row-shifted views of the input), the 1x1 conv [rows, F] x [F, F]
+// — done as 3xTF32 mma.sync (hi/lo split of both operands, fp32-level accuracy, same scheme as the stage-1 projection).  A CTA walks
+// 128-row tiles; the three shifted input tiles arrive by cp.async with rows before the video start zero-filled (= the causal left
+// padding, per row, so batched videos never see each other); weights (pre-split on the host) stay in shared memory for all tiles.
+// The fp32 SIMT kernel below it is bound by broadcast LDS of the weights (20 TFLOP/s); this one by the L2 stream of the activations.
+constexpr int kTcLdW = 40;                                                       // F + 8: conflict-free B fragments
+constexpr int kTcWpack = 2 * (96 * kTcLdW) + 2 * (32 * kTcLdW) + 64;             // Wd hi | Wd lo | W1 hi | W1 lo | bd | b1
+__global__ void __launch_bounds__(128) mstcn_layer_tc_kernel(const float* __restrict__ x, const int* __restrict__ frame_start, const float* __restrict__ wpack,
+                                                             int dilation, int64_t T, float* __restrict__ y, int num_tiles) {
+  constexpr int F = 32, BM = 128, LDA = F + 4, LDW = kTcLdW;
+  extern __shared__ __align__(16) float sm[];
+  float* Xs = sm;                         // [3 taps][BM][LDA]
+  float* Ws = Xs + 3 * BM * LDA;          // kTcWpack
+  float* Hs = Ws + kTcWpack;              // [4 warps][32][LDA]: relu(conv_dilated) of the warp's rows, A operand of the 1x1 conv
+  const float* Wdh = Ws;
+  const float* Wdl = Wdh + 96 * LDW;
+  const float* W1h = Wdl + 96 * LDW;
+  const float* W1l = W1h + 32 * LDW;
+  const float* bd = W1l + 32 * LDW;
+  const float* b1 = bd + F;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  for (int i = tid; i < kTcWpack / 4; i += 128) reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(wpack) + i);
+  float* hs = Hs + warp * 32 * LDA;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = static_cast<int64_t>(tile) * BM;
+    __syncthreads();   // the previous tile's reads of Xs are done (and, first time round, Ws is complete)
+    for (int i = tid; i < 3 * BM * (F / 4); i += 128) {
+      const int tap = i / (BM * (F / 4)), rem = i - tap * (BM * (F / 4)), r = rem >> 3, c4 = rem & 7;
+      const int64_t tt = row0 + r;
+      const int64_t ts = tt - static_cast<int64_t>(2 - tap) * dilation;
+      const bool ok = tt < T && ts >= static_cast<int64_t>(frame_start[tt < T ? tt : T - 1]);   // zero left padding, never across a video boundary
+      cp_async_16(Xs + (tap * BM + r) * LDA + c4 * 4, ok ? x + ts * F + c4 * 4 : x, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float acc[2][4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float2 b = *reinterpret_cast<const float2*>(bd + nt * 8 + t * 2);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) { acc[m][nt][0] = b.x; acc[m][nt][1] = b.y; acc[m][nt][2] = b.x; acc[m][nt][3] = b.y; }
+    }
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const float* a_s = Xs + (tap * BM + warp * 32) * LDA;
+#pragma unroll
+      for (int kk = 0; kk < F / 8; ++kk) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float* am = a_s + m * 16 * LDA + kk * 8;
+          const float a[4] = {am[g * LDA + t], am[(g + 8) * LDA + t], am[g * LDA + t + 4], am[(g + 8) * LDA + t + 4]};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ah[m][j] = to_tf32(a[j]);
+            al[m][j] = to_tf32(a[j] - __uint_as_float(ah[m][j]));
+          }
+        }
+        const int k0 = tap * F + kk * 8;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t bh0 = __float_as_uint(Wdh[(k0 + t) * LDW + nt * 8 + g]), bh1 = __float_as_uint(Wdh[(k0 + t + 4) * LDW + nt * 8 + g]);
+          const uint32_t bl0 = __float_as_uint(Wdl[(k0 + t) * LDW + nt * 8 + g]), bl1 = __float_as_uint(Wdl[(k0 + t + 4) * LDW + nt * 8 + g]);
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            mma_tf32_1688(acc[m][nt], al[m], bh0, bh1);   // small terms first
+            mma_tf32_1688(acc[m][nt], ah[m], bl0, bl1);
+            mma_tf32_1688(acc[m][nt], ah[m], bh0, bh1);
+          }
+        }
+      }
+    }
+    // h = relu(.) -> the warp's scratch rows (accumulator layout -> A-operand layout goes through shared memory)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(hs + (m * 16 + g) * LDA + nt * 8 + t * 2) = make_float2(fmaxf(acc[m][nt][0], 0.f), fmaxf(acc[m][nt][1], 0.f));
+        *reinterpret_cast<float2*>(hs + (m * 16 + g + 8) * LDA + nt * 8 + t * 2) = make_float2(fmaxf(acc[m][nt][2], 0.f), fmaxf(acc[m][nt][3], 0.f));
+      }
+    __syncwarp();
+    // out = x[t] + b1 + W1 h   (x[t] is the tap-2 tile)
+    const float* x_s = Xs + (2 * BM + warp * 32) * LDA;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 b = *reinterpret_cast<const float2*>(b1 + nt * 8 + t * 2);
+        const float2 x0 = *reinterpret_cast<const float2*>(x_s + (m * 16 + g) * LDA + nt * 8 + t * 2);
+        const float2 x1 = *reinterpret_cast<const float2*>(x_s + (m * 16 + g + 8) * LDA + nt * 8 + t * 2);
+        acc[m][nt][0] = x0.x + b.x; acc[m][nt][1] = x0.y + b.y; acc[m][nt][2] = x1.x + b.x; acc[m][nt][3] = x1.y + b.y;
+      }
+#pragma unroll
+    for (int kk = 0; kk < F / 8; ++kk) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const float* am = hs + m * 16 * LDA + kk * 8;
+        const float a[4] = {am[g * LDA + t], am[(g + 8) * LDA + t], am[g * LDA + t + 4], am[(g + 8) * LDA + t + 4]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ah[m][j] = to_tf32(a[j]);
+          al[m][j] = to_tf32(a[j] - __uint_as_float(ah[m][j]));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t bh0 = __float_as_uint(W1h[(kk * 8 + t) * LDW + nt * 8 + g]), bh1 = __float_as_uint(W1h[(kk * 8 + t + 4) * LDW + nt * 8 + g]);
+        const uint32_t bl0 = __float_as_uint(W1l[(kk * 8 + t) * LDW + nt * 8 + g]), bl1 = __float_as_uint(W1l[(kk * 8 + t + 4) * LDW + nt * 8 + g]);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          mma_tf32_1688(acc[m][nt], al[m], bh0, bh1);
+          mma_tf32_1688(acc[m][nt], ah[m], bl0, bl1);
+          mma_tf32_1688(acc[m][nt], ah[m], bh0, bh1);
+        }
+      }
+    }
+    __syncwarp();   // every lane has read hs before the next tile overwrites it
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int64_t r0 = row0 + warp * 32 + m * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (r0 < T) *reinterpret_cast<float2*>(y + r0 * F + nt * 8 + t * 2) = make_float2(acc[m][nt][0], acc[m][nt][1]);
+        if (r1 < T) *reinterpret_cast<float2*>(y + r1 * F + nt * 8 + t * 2) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+      }
+    }
+  }
+}
+
 // ---- conv_out_classes (mstcn.py:177): logits[c, t] = Wout[c,:] . h[t,:] + b[c]; channel-major output (coalesced over t).
 // Optionally fused with the next stage's softmax(dim=channels) + conv_1x1 (mstcn.py:126, 174): next[t, f].
 template <int F>
@@ -321,7 +456,7 @@ struct sv_mstcn {
   bool packed = false;
   float* d_weights = nullptr;  // single device blob
   // offsets (in floats) into the blob
-  struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next, w_in_hi = 0, w_in_lo = 0; std::vector<size_t> layer; };
+  struct Stage { size_t w_in, b_in, w_out, b_out, w_next, b_next, w_in_hi = 0, w_in_lo = 0; std::vector<size_t> layer, layer_tc; };
   std::vector<Stage> stages;
   int q_out = 0;  // rows of the optional query head `fc.weight` packed next to the stage-1 projection (0 = absent)
   int64_t launches = 0;
@@ -370,6 +505,11 @@ int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n
   constexpr int NS = 1;  // time steps per thread in the layer kernel (NS = 2 measured slower on B200: 167 registers, 92 vs 76 us)
   const unsigned lb = static_cast<unsigned>(ceil_div64(ceil_div64(T, NS), 128));
   SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mstcn_layer_kernel<F, NS>), static_cast<int>(layer_smem)));
+  static const bool use_tc = [] { const char* e = getenv("SURGVID_MSTCN_TC"); return !(e && atoi(e) == 0); }();   // A/B switch
+  const size_t tc_smem = (3 * 128 * (32 + 4) + kTcWpack + 4 * 32 * (32 + 4)) * sizeof(float);
+  const int tc_tiles = static_cast<int>(ceil_div64(T, 128));
+  const int tc_grid = std::min(tc_tiles, 2 * std::max(1, device_sm_count()));
+  if (F == 32 && use_tc) SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(mstcn_layer_tc_kernel), static_cast<int>(tc_smem)));
   float* cur = bufA;  // current stage input / running activation
   float* nxt = bufB;
   for (int s = 0; s < c.stages; ++s) {
@@ -380,8 +520,13 @@ int run_forward(sv_mstcn* h, const float* feats, const int64_t* d_offsets, int n
       ++h->launches;
     }
     for (int l = 0; l < c.layers; ++l) {
-      mstcn_layer_kernel<F, NS><<<lb, 128, layer_smem, st>>>(cur, frame_start, W + S.layer[l], 1 << l, T, nxt);
-      SV_TRY(launch_status("mstcn_layer_kernel"));
+      if (F == 32 && use_tc) {
+        mstcn_layer_tc_kernel<<<tc_grid, 128, tc_smem, st>>>(cur, frame_start, W + S.layer_tc[l], 1 << l, T, nxt, tc_tiles);
+        SV_TRY(launch_status("mstcn_layer_tc_kernel"));
+      } else {
+        mstcn_layer_kernel<F, NS><<<lb, 128, layer_smem, st>>>(cur, frame_start, W + S.layer[l], 1 << l, T, nxt);
+        SV_TRY(launch_status("mstcn_layer_kernel"));
+      }
       ++h->launches;
       std::swap(cur, nxt);
     }
@@ -509,6 +654,34 @@ int sv_mstcn_pack_weights(sv_mstcn_handle* h) {
         for (int64_t co = 0; co < F; ++co) blob[o1 + ci * F + co] = w1->data[co * F + ci];
       std::copy(bd->data.begin(), bd->data.end(), blob.begin() + o1 + F * F);
       std::copy(b1->data.begin(), b1->data.end(), blob.begin() + o1 + F * F + F);
+      if (F == 32) {  // tensor-core layer kernel: [k][n] rows padded to kTcLdW, TF32 hi/lo pre-split
+        auto tf32_rna = [](float x) {
+          uint32_t u;
+          memcpy(&u, &x, 4);
+          u = (u + 0x1000u) & 0xFFFFE000u;
+          float r;
+          memcpy(&r, &u, 4);
+          return r;
+        };
+        const size_t ot = reserve(kTcWpack);
+        S.layer_tc.push_back(ot);
+        const size_t dh = ot, dl = dh + 96 * kTcLdW, oh = dl + 96 * kTcLdW, ol = oh + 32 * kTcLdW, obd = ol + 32 * kTcLdW, ob1 = obd + 32;
+        for (int64_t k = 0; k < 3; ++k)
+          for (int64_t ci = 0; ci < F; ++ci)
+            for (int64_t co = 0; co < F; ++co) {
+              const float w = wd->data[(co * F + ci) * 3 + k], hi = tf32_rna(w);
+              blob[dh + (k * F + ci) * kTcLdW + co] = hi;
+              blob[dl + (k * F + ci) * kTcLdW + co] = tf32_rna(w - hi);
+            }
+        for (int64_t ci = 0; ci < F; ++ci)
+          for (int64_t co = 0; co < F; ++co) {
+            const float w = w1->data[co * F + ci], hi = tf32_rna(w);
+            blob[oh + ci * kTcLdW + co] = hi;
+            blob[ol + ci * kTcLdW + co] = tf32_rna(w - hi);
+          }
+        std::copy(bd->data.begin(), bd->data.end(), blob.begin() + obd);
+        std::copy(b1->data.begin(), b1->data.end(), blob.begin() + ob1);
+      }
     }
     SV_TRY(expect(h, p + ".conv_out_classes.weight", {C, F, 1}, &w));
     SV_TRY(expect(h, p + ".conv_out_classes.bias", {C}, &b));
