@@ -394,6 +394,215 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
+// ---- N_kv <= 64, persistent: a CTA walks a contiguous range of (frame, head, query tile) work items, so the per-CTA set-up (TMEM
+// allocation, barrier init, descriptor prefetch) is paid once per SM slot instead of once per one or two tiles (stages 3 and 4 have
+// 196 / 49 queries per frame and head), and the K/V tiles of the NEXT (frame, head) are prefetched into a second buffer while the
+// current one is being used.  Tile j of the CTA belongs to softmax group j & 1 (ping-pong, S and O double-buffered in TMEM).
+struct AttnTcSingleParams {
+  int Nq, Nkv, heads, qtiles, tiles_total;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                           const __grid_constant__ CUtensorMap tmap_o, const AttnTcSingleParams p) {
+  extern __shared__ uint8_t attn_tc_smem[];
+  __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], q_full[2], q_empty[2], s_full[2], p_full[2], o_full[2], o_staged[2], st_done[2];
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kTmemCols = 256;   // S of group g at 64g, O of group g at 128 + 64g
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = p.tiles_total / static_cast<int>(gridDim.x), extra = p.tiles_total % static_cast<int>(gridDim.x);
+  const int t_begin = static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), extra);
+  const int ntiles = per + (static_cast<int>(blockIdx.x) < extra ? 1 : 0);
+  uint8_t* smem = attn_tc_smem + ((1024u - (ptx::smem_u32(attn_tc_smem) & 1023u)) & 1023u);
+  uint8_t* Qs = smem;                       // [2][16 KB]
+  uint8_t* Ks = Qs + 2 * kQBytes;           // [2][8 KB]  K of the current / the next (frame, head)
+  uint8_t* Vs = Ks + 2 * kKBytes;           // [2][8 KB]
+  uint8_t* Ps = Vs + 2 * kKBytes;           // [2][16 KB]; a consumed P buffer doubles as the staging tile of the output
+
+  if (warp == 8 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_q);
+    ptx::prefetch_tensormap(&tmap_k);
+    ptx::prefetch_tensormap(&tmap_v);
+    ptx::prefetch_tensormap(&tmap_o);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&kv_full[i], 1);
+        ptx::mbar_init(&kv_empty[i], 1);
+        ptx::mbar_init(&q_full[i], 1);
+        ptx::mbar_init(&q_empty[i], 1);
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&p_full[i], 128);
+        ptx::mbar_init(&o_full[i], 1);
+        ptx::mbar_init(&o_staged[i], 128);
+        ptx::mbar_init(&st_done[i], 1);
+      }
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_o = tmem_base + 2u * kKeys;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");   // one instruction for the whole control warpgroup; 8 * 96 + 4 * 48 = 12 * 80
+    if (warp == 8) {
+      // ---------------------------------------------------------------- TMA loads
+      if (lane == 0) {
+        int prev_bh = -1, n_kv = 0;
+        for (int j = 0; j < ntiles; ++j) {
+          const int t = t_begin + j, bh = t / p.qtiles, qt = t - bh * p.qtiles, b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
+          if (bh != prev_bh) {
+            const int kb = n_kv & 1;
+            if (n_kv >= 2) ptx::mbar_wait(&kv_empty[kb], static_cast<uint32_t>(((n_kv - 2) >> 1) & 1));   // every MMA on the pair two back has retired
+            ptx::mbar_arrive_expect_tx(&kv_full[kb], 2 * kKBytes);
+            tma_load_3d(Ks + kb * kKBytes, &tmap_k, &kv_full[kb], c0, 0, b);
+            tma_load_3d(Vs + kb * kKBytes, &tmap_v, &kv_full[kb], c0, 0, b);
+            ++n_kv;
+            prev_bh = bh;
+          }
+          const int qb = j & 1;
+          if (j >= 2) ptx::mbar_wait(&q_empty[qb], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // the S MMAs of tile j-2 have read this buffer
+          ptx::mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+          tma_load_3d(Qs + qb * kQBytes, &tmap_q, &q_full[qb], c0, qt * kQRows, b);
+        }
+      }
+    } else if (warp == 10) {
+      // ---------------------------------------------------------------- TMA stores of the output tiles (warp 11 idles)
+      if (lane == 0) {
+        for (int j = 0; j < ntiles; ++j) {
+          const int t = t_begin + j, bh = t / p.qtiles, qt = t - bh * p.qtiles, b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
+          const int sb = j & 1;
+          ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((j >> 1) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+          tma_store_3d(&tmap_o, Ps + sb * kQBytes, c0, qt * kQRows, b);
+          tma_store_commit();
+          tma_store_wait_read();                  // the store has read the buffer: P may be overwritten / the CTA may exit
+          ptx::mbar_arrive(&st_done[sb]);
+        }
+      }
+    } else if (warp == 9) {
+      // ---------------------------------------------------------------- MMA issuer (single thread)
+      if (lane == 0) {
+        const uint32_t idesc_s = ptx::make_idesc_bf16_f32(kQRows, kKeys);                 // A, B K-major
+        const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(kQRows, kHD) | (1u << 16);     // B (= V) MN-major
+        // issue order S_0, S_1, PV_0, S_2, PV_1, ...: the S MMA of the next tile is in flight while a group does its exponentials
+        int n_kv = 0, bh_s = -1, kb_s = 0;   // K/V buffer of the tile whose S is being issued
+        int bh_pv = -1, kb_pv = 0;           // ... and of the tile whose PV is being issued (one tile behind)
+        for (int j = 0; j <= ntiles; ++j) {
+          if (j < ntiles) {
+            const int bh = (t_begin + j) / p.qtiles;
+            if (bh != bh_s) {
+              kb_s = n_kv & 1;
+              ptx::mbar_wait(&kv_full[kb_s], static_cast<uint32_t>((n_kv >> 1) & 1));
+              ++n_kv;
+              bh_s = bh;
+            }
+            const int g = j & 1;
+            ptx::mbar_wait(&q_full[g], static_cast<uint32_t>((j >> 1) & 1));
+            ptx::tc_fence_after();
+            const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + g * kQBytes));
+            const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + kb_s * kKBytes));
+#pragma unroll
+            for (int ks = 0; ks < kHD / 16; ++ks)
+              ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+            ptx::umma_commit(&s_full[g]);
+            ptx::umma_commit(&q_empty[g]);
+          }
+          if (j >= 1) {
+            const int jj = j - 1, g = jj & 1;
+            const int bh = (t_begin + jj) / p.qtiles;
+            if (bh != bh_pv) { kb_pv = (bh_pv < 0) ? 0 : (kb_pv ^ 1); bh_pv = bh; }   // pairs alternate buffers in issue order
+            // P_jj is in shared memory; the same arrivals order the group's reads of S_jj and of O_{jj-2} before this point
+            ptx::mbar_wait(&p_full[g], static_cast<uint32_t>((jj >> 1) & 1));
+            ptx::tc_fence_after();
+            const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + g * kQBytes));
+            const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs + kb_pv * kKBytes));
+#pragma unroll
+            for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
+              ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
+                            ks ? 1u : 0u);
+            ptx::umma_commit(&o_full[g]);
+            // last tile of its (frame, head): once everything issued so far has retired, the K/V buffer may be refilled
+            if (j == ntiles || (t_begin + j) / p.qtiles != bh) ptx::umma_commit(&kv_empty[kb_pv]);
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output rows (thread = query row = TMEM lane)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + static_cast<uint32_t>(grp * kKeys) + lane_sel;
+    const uint32_t t_o = tmem_o + static_cast<uint32_t>(grp * kHD) + lane_sel;
+    uint8_t* Pg = Ps + grp * kQBytes;
+    for (int j = grp; j < ntiles; j += 2) {
+      const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
+      const int qt = (t_begin + j) % p.qtiles;
+      const bool active = qt * kQRows + quarter * 32 < p.Nq;   // warp-uniform: rows past the frame's last query do no math
+      ptx::mbar_wait(&s_full[grp], par);
+      ptx::tc_fence_after();
+      float l = 1.f;
+      if (active) {
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_x32(t_s, r0);
+        ptx::tmem_ld_x32(t_s + 32u, r1);
+        ptx::tmem_ld_wait();
+        float m = max32(r0, 0, p.Nkv, -INFINITY);
+        m = max32(r1, 32, p.Nkv, m) * p.scale_log2;   // scale > 0: max commutes with it
+        uint32_t w[16];
+        l = exp32(r0, 0, p.Nkv, p.scale_log2, m, w);
+        // P buffer `grp` is free: the PV MMAs of this group's previous tile retired before its o_full, and the TMA store of that
+        // tile's output (staged in the same buffer) has finished reading it
+        if (j >= 2) ptx::mbar_wait(&st_done[grp], static_cast<uint32_t>(((j - 2) >> 1) & 1));
+        store_half_row_sw128(Pg, row, 0, w);
+        l += exp32(r1, 32, p.Nkv, p.scale_log2, m, w);
+        store_half_row_sw128(Pg, row, 4, w);
+      }
+      ptx::fence_proxy_async_smem();   // generic-proxy stores of P -> visible to the tensor core
+      ptx::tc_fence_before();          // this thread's TMEM reads of S are complete
+      ptx::mbar_arrive(&p_full[grp]);
+      ptx::mbar_wait(&o_full[grp], par);
+      ptx::tc_fence_after();
+      if (active) {
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_x32(t_o, r0);
+        ptx::tmem_ld_x32(t_o + 32u, r1);
+        ptx::tmem_ld_wait();
+        const float inv = 1.0f / l;
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) w[i >> 1] = pack_bf16x2(__uint_as_float(r0[i]) * inv, __uint_as_float(r0[i + 1]) * inv);
+        store_half_row_sw128(Pg, row, 0, w);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) w[i >> 1] = pack_bf16x2(__uint_as_float(r1[i]) * inv, __uint_as_float(r1[i + 1]) * inv);
+        store_half_row_sw128(Pg, row, 4, w);
+      } else if (j >= 2) {
+        ptx::mbar_wait(&st_done[grp], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // keep the phase bookkeeping of idle warps in step
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&o_staged[grp]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -472,8 +681,16 @@ int attention_tc_launch(const AttnTcPlan& plan, cudaStream_t st) {
     SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<true>), 2 * kQBytes + 2 * kMaxKt * kKBytes + 2 * kQBytes + 1024));
     attention_tc_kernel<true><<<grid, kThreads, plan.smem_bytes, st>>>(plan.tmap_q, plan.tmap_k, plan.tmap_v, plan.tmap_o, p);
   } else {
-    SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel<false>), 4 * kQBytes + 2 * kKBytes + 1024));
-    attention_tc_kernel<false><<<grid, kThreads, plan.smem_bytes, st>>>(plan.tmap_q, plan.tmap_k, plan.tmap_v, plan.tmap_o, p);
+    AttnTcSingleParams sp;
+    sp.Nq = plan.Nq; sp.Nkv = plan.Nkv; sp.heads = plan.heads; sp.qtiles = plan.qtiles; sp.scale_log2 = plan.scale_log2;
+    const long long total = static_cast<long long>(plan.B) * plan.heads * plan.qtiles;
+    if (total >= (1LL << 31)) return fail(SV_ERR_INVALID, "attention_tc: more than 2^31 query tiles");
+    sp.tiles_total = static_cast<int>(total);
+    const int smem_single = 4 * kQBytes + 4 * kKBytes + 1024;
+    SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_single_kernel), smem_single));
+    // persistent: two CTAs per SM, each walking a contiguous range of >= 2 tiles (one per softmax group)
+    const int grid1 = static_cast<int>(std::min<long long>(std::max<long long>(1, (total + 1) / 2), 2LL * std::max(1, device_sm_count())));
+    attention_tc_single_kernel<<<grid1, kThreads, smem_single, st>>>(plan.tmap_q, plan.tmap_k, plan.tmap_v, plan.tmap_o, sp);
   }
   return launch_status("attention_tc_kernel");
 }
