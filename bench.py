@@ -318,10 +318,18 @@ class Ctx:
         model, T = self.model, x.shape[0]
         h = model._native[self.local]["handle"]
         lib.sv_evp_set_profile(h, 1)
+        ncu_range = bool(os.environ.get("SURGVID_NCU_RANGE"))   # `ncu --profile-from-start off` then captures exactly this pass
+        if ncu_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         with torch.no_grad():
             for b0 in range(0, T, B):
                 model(x[b0:min(T, b0 + B)], seg[b0:min(T, b0 + B)], flow[b0:min(T, b0 + B)], return_features=True)
+            if ncu_range:
+                self.tcn.forward_videos(torch.zeros((T, 2048), device=self.dev), [T])
         torch.cuda.synchronize()
+        if ncu_range:
+            torch.cuda.profiler.stop()
         ms_k = (ctypes.c_double * 16)()
         n_k = (ctypes.c_int64 * 16)()
         fl = ctypes.c_double(0)

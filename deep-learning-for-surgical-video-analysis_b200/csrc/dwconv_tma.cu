@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -19,12 +20,12 @@ namespace {
 
 constexpr int kTW = 8;          // max output columns per tile (= consumer warps); 7 or 8 are used, whichever tiles W exactly
 constexpr int kTH = 7;          // output rows per tile
-constexpr int kCB = 128;        // channels per tile (32 lanes x 4)
+constexpr int kCB = 128;        // channels per tile with 4 channels per lane (CPL = 4); CPL = 2 -> 64-channel tiles
 constexpr int kStages = 4;
 constexpr int kPrefetch = 2;      // tiles in flight ahead of the one being computed; < kStages - 1 so that the producer lane
                                   // re-fills a stage released a whole tile ago and never waits for the slowest warp
 constexpr int kBoxW = kTW + 2, kBoxH = kTH + 2;
-constexpr int kTileBytes = kBoxH * kBoxW * kCB * 2;  // 23 040
+constexpr int kTileBytes = kBoxH * kBoxW * kCB * 2;  // 23 040 (CPL = 4); half of it for CPL = 2
 constexpr int kThreads = 32 * kTW;  // 8 warps: 2 CTAs/SM -> 4 warps per scheduler -> 128 registers per thread available
 
 struct DwParams {
@@ -44,9 +45,14 @@ struct DwParams {
 // 2 = 0.5 x (1 + tanh(g(x))), one MUFU.TANH per element (default: measured 16 % faster than 0 and 9 % faster than 1 at every stage
 // shape; end-to-end LFB parity vs the reference goldens is unchanged to three digits — rel-L2 2.10e-3 / 3.43e-3 (0), 2.06e-3 /
 // 3.39e-3 (1), 2.11e-3 / 3.40e-3 (2) — because the bf16 rounding of the stored result is an order of magnitude coarser)
-template <int GELU>
-__global__ void __launch_bounds__(kThreads, 2)
+// CPL = channels per lane: 4 (128-channel tiles, 2 CTAs/SM at 128 registers) or 2 (64-channel tiles, half the registers per thread
+// for window + weights -> 4 CTAs/SM = 32 warps: the kernel is latency-bound, not bandwidth-bound, at 16 warps per SM)
+template <int GELU, int CPL>
+__global__ void __launch_bounds__(kThreads, CPL == 4 ? 2 : 4)
 dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwParams p) {
+  constexpr int CB = 32 * CPL, NP = CPL / 2;          // channels per tile, f32x2 pairs per lane
+  constexpr int kTileB = kBoxH * kBoxW * CB * 2;
+  typedef typename std::conditional<CPL == 4, uint2, uint32_t>::type LaneWord;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
@@ -76,8 +82,8 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
     const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
     ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
     tile_coord[stage] = make_int4(cblk, tx, ty, b);  // visible to the consumers through the barrier's release/acquire
-    ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBoxH * (p.tw + 2) * kCB * 2));
-    ptx::tma_load_4d(smem + stage * kTileBytes, &tmap_x, &full_bar[stage], cblk * kCB, tx * p.tw - 1, ty * kTH - 1, b);
+    ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kBoxH * (p.tw + 2) * CB * 2));
+    ptx::tma_load_4d(smem + stage * kTileB, &tmap_x, &full_bar[stage], cblk * CB, tx * p.tw - 1, ty * kTH - 1, b);
   };
   // each CTA walks one contiguous range of tiles: neighbouring tiles (shared halos) are loaded back to back and the
   // 128-channel weight block in registers changes at most a couple of times per CTA
@@ -99,8 +105,10 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   int stage = 0;
   uint32_t phase = 0;
   int cur_cblk = -1;
-  f32x2 wt[9][2];
-  f32x2 bias0 = 0, bias1 = 0;
+  f32x2 wt[9][NP];
+  f32x2 biasv[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) biasv[q] = 0;
   for (int t = t_begin; t < t_end; ++t) {
     if (is_producer && pt < t_end) {
       issue_tile(pt, pstage, pphase);
@@ -112,33 +120,47 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       ptx::mbar_wait(&full_bar[stage], phase);
       const int4 tc = tile_coord[stage];
       const int cblk = tc.x, tx = tc.y, ty = tc.z, b = tc.w;
-      const int c0 = cblk * kCB + lane * 4;
+      const int c0 = cblk * CB + lane * CPL;
       if (cblk != cur_cblk) {  // weights of this 128-channel block stay in registers across tiles
         cur_cblk = cblk;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w9c + tap * p.C + c0));
-          wt[tap][0] = f2_pack(w4.x, w4.y);
-          wt[tap][1] = f2_pack(w4.z, w4.w);
+          if constexpr (CPL == 4) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w9c + tap * p.C + c0));
+            wt[tap][0] = f2_pack(w4.x, w4.y);
+            wt[tap][NP - 1] = f2_pack(w4.z, w4.w);
+          } else {
+            const float2 w2 = __ldg(reinterpret_cast<const float2*>(p.w9c + tap * p.C + c0));
+            wt[tap][0] = f2_pack(w2.x, w2.y);
+          }
         }
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-        bias0 = f2_pack(b4.x, b4.y);
-        bias1 = f2_pack(b4.z, b4.w);
+        if constexpr (CPL == 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+          biasv[0] = f2_pack(b4.x, b4.y);
+          biasv[NP - 1] = f2_pack(b4.z, b4.w);
+        } else {
+          const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c0));
+          biasv[0] = f2_pack(b2.x, b2.y);
+        }
       }
       const int w = tx * p.tw + col;
       const int h0 = ty * kTH;
-      // smem tile: [kBoxH][boxw][128 ch] bf16; this thread reads box columns col, col+1, col+2
-      const uint2* tile = reinterpret_cast<const uint2*>(smem + stage * kTileBytes) + col * (kCB / 4) + lane;
-      const int row_words = boxw * (kCB / 4);
-      auto load_row = [&](int br, f32x2 (&dst)[3][2]) {
+      // smem tile: [kBoxH][boxw][CB ch] bf16; this thread reads box columns col, col+1, col+2
+      const LaneWord* tile = reinterpret_cast<const LaneWord*>(smem + stage * kTileB) + col * 32 + lane;
+      const int row_words = boxw * 32;
+      auto load_row = [&](int br, f32x2 (&dst)[3][NP]) {
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const uint2 v = tile[br * row_words + dx * (kCB / 4)];
-          dst[dx][0] = f2_from_bf16x2(v.x);
-          dst[dx][1] = f2_from_bf16x2(v.y);
+          const LaneWord v = tile[br * row_words + dx * 32];
+          if constexpr (CPL == 4) {
+            dst[dx][0] = f2_from_bf16x2(v.x);
+            dst[dx][NP - 1] = f2_from_bf16x2(v.y);
+          } else {
+            dst[dx][0] = f2_from_bf16x2(v);
+          }
         }
       };
-      f32x2 ring[3][3][2];
+      f32x2 ring[3][3][NP];
       load_row(0, ring[0]);
       load_row(1, ring[1]);
       bf16* optr = p.out + ((static_cast<long long>(b) * p.H + h0) * p.W + w) * p.ldo + c0;
@@ -146,37 +168,42 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
 #pragma unroll
       for (int i = 0; i < kTH; ++i) {
         load_row(i + 2, ring[(i + 2) % 3]);
-        // three independent 3-tap chains per accumulator (one per window row) instead of one 9-deep chain: the kernel runs at 16 warps
-        // per SM, so instruction-level parallelism inside a warp is what hides the FFMA2 latency
-        f32x2 s0[3], s1[3];
+        // three independent 3-tap chains per accumulator (one per window row) instead of one 9-deep chain
+        f32x2 a[NP];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          s0[dy] = f2_fma(ring[(i + dy) % 3][0][0], wt[dy * 3][0], dy == 0 ? bias0 : f2_mul(ring[(i + dy) % 3][1][0], wt[dy * 3 + 1][0]));
-          s1[dy] = f2_fma(ring[(i + dy) % 3][0][1], wt[dy * 3][1], dy == 0 ? bias1 : f2_mul(ring[(i + dy) % 3][1][1], wt[dy * 3 + 1][1]));
-          if (dy == 0) {
-            s0[dy] = f2_fma(ring[(i + dy) % 3][1][0], wt[dy * 3 + 1][0], s0[dy]);
-            s1[dy] = f2_fma(ring[(i + dy) % 3][1][1], wt[dy * 3 + 1][1], s1[dy]);
+        for (int q = 0; q < NP; ++q) {
+          f32x2 sacc[3];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const f32x2 (&rr)[3][NP] = ring[(i + dy) % 3];
+            f32x2 t = dy == 0 ? f2_fma(rr[1][q], wt[1][q], biasv[q]) : f2_mul(rr[1][q], wt[dy * 3 + 1][q]);
+            t = f2_fma(rr[0][q], wt[dy * 3][q], t);
+            sacc[dy] = f2_fma(rr[2][q], wt[dy * 3 + 2][q], t);
           }
-          s0[dy] = f2_fma(ring[(i + dy) % 3][2][0], wt[dy * 3 + 2][0], s0[dy]);
-          s1[dy] = f2_fma(ring[(i + dy) % 3][2][1], wt[dy * 3 + 2][1], s1[dy]);
+          a[q] = f2_add(f2_add(sacc[0], sacc[1]), sacc[2]);
         }
-        f32x2 a0 = f2_add(f2_add(s0[0], s0[1]), s0[2]), a1 = f2_add(f2_add(s1[0], s1[1]), s1[2]);
         if constexpr (GELU == 0) {
-          f2_gelu_erf_poly_x2(a0, a1);
-        } else if constexpr (GELU == 1) {
-          a0 = f2_gelu_sigmoid(a0);
-          a1 = f2_gelu_sigmoid(a1);
+          if constexpr (CPL == 4) f2_gelu_erf_poly_x2(a[0], a[NP - 1]);
+          else a[0] = f2_gelu_erf_poly(a[0]);
         } else {
-          a0 = f2_gelu_tanh(a0);
-          a1 = f2_gelu_tanh(a1);
+#pragma unroll
+          for (int q = 0; q < NP; ++q) a[q] = GELU == 1 ? f2_gelu_sigmoid(a[q]) : f2_gelu_tanh(a[q]);
         }
-        float y0, y1, y2, y3;
-        f2_unpack(a0, y0, y1);
-        f2_unpack(a1, y2, y3);
-        uint2 o;
-        o.x = pack_bf16x2(y0, y1);
-        o.y = pack_bf16x2(y2, y3);
-        if (i < rows_ok) *reinterpret_cast<uint2*>(optr) = o;
+        if (i < rows_ok) {
+          if constexpr (CPL == 4) {
+            float y0, y1, y2, y3;
+            f2_unpack(a[0], y0, y1);
+            f2_unpack(a[NP - 1], y2, y3);
+            uint2 o;
+            o.x = pack_bf16x2(y0, y1);
+            o.y = pack_bf16x2(y2, y3);
+            *reinterpret_cast<uint2*>(optr) = o;
+          } else {
+            float y0, y1;
+            f2_unpack(a[0], y0, y1);
+            *reinterpret_cast<uint32_t*>(optr) = pack_bf16x2(y0, y1);
+          }
+        }
         optr += p.row_stride;
       }
       __syncwarp();
@@ -204,6 +231,10 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
+static int dw_cpl() {
+  static const int cpl = [] { const char* e = getenv("SURGVID_DW_CPL"); const int v = e ? atoi(e) : 4; return v == 2 ? 2 : 4; }();
+  return cpl;
+}
 bool dwconv_tma_supported(int C) { return C % kCB == 0; }
 
 int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo, DwconvPlan* plan) {
@@ -215,31 +246,36 @@ int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, i
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2, static_cast<cuuint64_t>(H) * W * C * 2};
   const int tw = (W % 8 == 0) ? 8 : ((W % 7 == 0) ? 7 : 8);
-  cuuint32_t box[4] = {kCB, static_cast<cuuint32_t>(tw + 2), kBoxH, 1};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(32 * dw_cpl()), static_cast<cuuint32_t>(tw + 2), kBoxH, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(&plan->tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(dwconv) failed, CUresult " + std::to_string(static_cast<int>(r)));
   plan->w9c = w9c; plan->bias = bias; plan->out = out; plan->B = B; plan->H = H; plan->W = W; plan->C = C; plan->ldo = ldo; plan->tw = tw;
+  plan->cpl = dw_cpl();
   return SV_OK;
 }
 
 int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
-  constexpr int smem_bytes = kStages * kTileBytes + 128;
+  const int cb = 32 * plan.cpl;
+  const int smem_bytes = kStages * (kBoxH * kBoxW * cb * 2) + 128;
   static const int gelu_mode = [] { const char* e = getenv("SURGVID_DW_GELU"); return e ? atoi(e) : 2; }();
-  void (*kern)(const CUtensorMap, const DwParams) = gelu_mode == 0 ? dwconv3x3_gelu_tma_kernel<0> : (gelu_mode == 2 ? dwconv3x3_gelu_tma_kernel<2> : dwconv3x3_gelu_tma_kernel<1>);
+  typedef void (*KernFn)(const CUtensorMap, const DwParams);
+  KernFn kern;
+  if (plan.cpl == 4) kern = gelu_mode == 0 ? dwconv3x3_gelu_tma_kernel<0, 4> : (gelu_mode == 1 ? dwconv3x3_gelu_tma_kernel<1, 4> : dwconv3x3_gelu_tma_kernel<2, 4>);
+  else kern = gelu_mode == 0 ? dwconv3x3_gelu_tma_kernel<0, 2> : (gelu_mode == 1 ? dwconv3x3_gelu_tma_kernel<1, 2> : dwconv3x3_gelu_tma_kernel<2, 2>);
   SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem_bytes));
   DwParams p;
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tw = plan.tw;
-  p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / kCB;
+  p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / cb;
   const long long nt = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
   if (nt >= (1LL << 31)) return fail(SV_ERR_INVALID, "dwconv: more than 2^31 tiles");
   p.num_tiles = static_cast<int>(nt);
   p.tiles_per_cblk = plan.B * p.tiles_y * p.tiles_x;
   p.row_stride = static_cast<long long>(plan.W) * plan.ldo;
   const int sms = device_sm_count();
-  const int grid = static_cast<int>(std::min<long long>(p.num_tiles, 2LL * sms));
+  const int grid = static_cast<int>(std::min<long long>(p.num_tiles, (plan.cpl == 4 ? 2LL : 4LL) * sms));
   kern<<<grid, kThreads, smem_bytes, st>>>(plan.tmap, p);
   return launch_status("dwconv3x3_gelu_tma_kernel");
 }

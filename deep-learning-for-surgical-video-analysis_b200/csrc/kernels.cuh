@@ -41,6 +41,7 @@ struct DwconvPlan {
   int B = 0, H = 0, W = 0, C = 0;
   int64_t ldo = 0;  // output row (pixel) stride in elements, >= C
   int tw = 8;       // output columns per tile (box width - 2)
+  int cpl = 4;      // channels per lane: 4 (128-channel tiles) or 2 (64-channel tiles)
 };
 bool dwconv_tma_supported(int C);
 int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, int H, int W, int C, bf16* out, int64_t ldo, DwconvPlan* plan);

@@ -77,24 +77,27 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const StemParams p) {
     const int iy0 = oy0 * 4 - 3, ix0 = ox0 * 4 - 3;
     // ---- input patch -> smem (bf16), zero outside the image (= conv zero padding); warp = patch rows, lane = columns
     const float* sb = p.src + static_cast<int64_t>(b) * p.Cin * p.H * p.W;
-    // (loads are issued in batches of 11 per thread before any is consumed: ~11 x 128 B in flight per warp instead of one)
-    const int total = p.Cin * kPatch * kPs;
-#pragma unroll 1
-    for (int base_i = 0; base_i < total; base_i += 128 * 11) {
-      float v[11];
+    // warp = patch rows (yy = warp, warp + 4, ...), lane = patch columns: 32 consecutive floats of an image row per load (+ a 3-pixel
+    // tail), no per-element div/mod; the 9 row loads of a channel are issued before any is consumed (~9 x 128 B in flight per warp)
+    for (int c = 0; c < p.Cin; ++c) {
+      const float* sc = sb + static_cast<int64_t>(c) * p.H * p.W;
+      bf16* pc = Ps + c * kPatch * kPs;
+      float v0[9], v1[9];
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int i = base_i + j * 128 + tid;
-        const int r = i / kPs, xx = i - r * kPs;        // r = c*35 + yy
-        const int c = r / kPatch, yy = r - c * kPatch;
-        const int iy = iy0 + yy, ix = ix0 + xx;
-        v[j] = 0.f;
-        if (i < total && xx < kPatch && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v[j] = __ldg(sb + (static_cast<int64_t>(c) * p.H + iy) * p.W + ix);
+      for (int j = 0; j < 9; ++j) {
+        const int yy = warp + 4 * j, iy = iy0 + yy;
+        const bool rok = yy < kPatch && iy >= 0 && iy < p.H;
+        const int ix = ix0 + lane, ix2 = ix0 + 32 + lane;
+        v0[j] = (rok && ix >= 0 && ix < p.W) ? __ldg(sc + static_cast<int64_t>(iy) * p.W + ix) : 0.f;
+        v1[j] = (rok && lane < kPatch - 32 && ix2 < p.W) ? __ldg(sc + static_cast<int64_t>(iy) * p.W + ix2) : 0.f;   // ix2 >= 29 >= 0
       }
 #pragma unroll
-      for (int j = 0; j < 11; ++j) {
-        const int i = base_i + j * 128 + tid;
-        if (i < total) Ps[i] = __float2bfloat16(v[j]);
+      for (int j = 0; j < 9; ++j) {
+        const int yy = warp + 4 * j;
+        if (yy < kPatch) {
+          pc[yy * kPs + lane] = __float2bfloat16(v0[j]);
+          if (lane < kPs - 32) pc[yy * kPs + 32 + lane] = __float2bfloat16(v1[j]);   // columns 35..39 of the padded row are zero
+        }
       }
     }
     __syncthreads();

@@ -184,3 +184,24 @@ def test_480x854_three_frames_ragged_microbatch_vs_oracle():
     print(f"[parity] 480x854 B=3 mb=2 vs oracle: rel-L2 {rel:.3e}  max-abs {float((out.cpu() - ref).abs().max()):.3e}")
     assert rel <= 1.5e-2 and float((out.cpu() - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
     assert torch.equal(out, out3) and torch.equal(solo[0], out[2])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_same_process_second_gpu():
+    """One process, one model object, two devices (the DataParallel replica case): the per-device native handles opt their kernels in to
+    large dynamic shared memory on EACH device (the attribute is per device, not per process)."""
+    model, sd = _evp(mode="stress")
+    x, seg, flow = S.synth_frames(3, seed=88)
+    with torch.no_grad():
+        a = model(x.to("cuda:0"), seg.to("cuda:0"), flow.to("cuda:0"), return_features=True)
+        model.to("cuda:1")
+        with torch.cuda.device(1):
+            b = model(x.to("cuda:1"), seg.to("cuda:1"), flow.to("cuda:1"), return_features=True)
+            tcn = MultiStageModel_S(2, 8, 32, 2048, 14, True)
+            tcn.load_state_dict(S.synth_mstcn_state_dict(mode="phase"))
+            tcn = tcn.to("cuda:1").eval()
+            lg1 = tcn.forward_videos(b.repeat(20, 1), [60])
+        tcn = tcn.to("cuda:0")
+        lg0 = tcn.forward_videos(a.repeat(20, 1), [60])
+    model.to("cuda:0")
+    assert torch.equal(a.cpu(), b.cpu()) and torch.equal(lg0.cpu(), lg1.cpu())
