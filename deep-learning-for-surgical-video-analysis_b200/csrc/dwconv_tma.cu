@@ -21,7 +21,8 @@ namespace {
 constexpr int kTW = 8;          // max output columns per tile (= consumer warps); 7 or 8 are used, whichever tiles W exactly
 constexpr int kTH = 7;          // output rows per tile
 constexpr int kCB = 128;        // channels per tile with 4 channels per lane (CPL = 4); CPL = 2 -> 64-channel tiles
-constexpr int kStages = 4;
+constexpr int kMaxStages = 8;     // ring depth and prefetch distance are run-time (DwParams::stages / prefetch)
+constexpr int kStages = 4;        // defaults
 constexpr int kPrefetch = 2;      // tiles in flight ahead of the one being computed; < kStages - 1 so that the producer lane
                                   // re-fills a stage released a whole tile ago and never waits for the slowest warp
 constexpr int kBoxW = kTW + 2, kBoxH = kTH + 2;
@@ -36,6 +37,7 @@ struct DwParams {
   long long ldo;
   int tiles_x, tiles_y, cblks;
   int tw;  // output columns per tile actually used (<= kTW); box width = tw + 2
+  int stages, prefetch;  // shared-memory ring depth (<= kMaxStages) and tiles requested ahead of the one being computed
   int num_tiles;
   int tiles_per_cblk;
   long long row_stride;  // elements between vertically adjacent output pixels (W * ldo)
@@ -54,15 +56,15 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   constexpr int kTileB = kBoxH * kBoxW * CB * 2;
   typedef typename std::conditional<CPL == 4, uint2, uint32_t>::type LaneWord;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ int4 tile_coord[kStages];  // (cblk, tx, ty, b) of the tile in each stage, written by the producer
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ int4 tile_coord[kMaxStages];  // (cblk, tx, ty, b) of the tile in each stage, written by the producer
   uint8_t* smem = smem_raw + ((128u - (ptx::smem_u32(smem_raw) & 127u)) & 127u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tensormap(&tmap_x);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], p.tw);
     }
@@ -94,9 +96,9 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   int pt = t_begin, pstage = 0;  // producer cursor
   uint32_t pphase = 0;
   if (is_producer) {
-    for (int i = 0; i < kPrefetch && pt < t_end; ++i, ++pt) {
+    for (int i = 0; i < p.prefetch && pt < t_end; ++i, ++pt) {
       issue_tile(pt, pstage, pphase);
-      if (++pstage == kStages) { pstage = 0; pphase ^= 1u; }
+      if (++pstage == p.stages) { pstage = 0; pphase ^= 1u; }
     }
   }
   const int col = warp;
@@ -113,7 +115,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
     if (is_producer && pt < t_end) {
       issue_tile(pt, pstage, pphase);
       ++pt;
-      if (++pstage == kStages) { pstage = 0; pphase ^= 1u; }
+      if (++pstage == p.stages) { pstage = 0; pphase ^= 1u; }
     }
     __syncwarp();
     if (active) {
@@ -209,7 +211,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);  // this warp is done reading the stage
     }
-    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
   }
 }
 
@@ -258,7 +260,11 @@ int dwconv_tma_plan(const bf16* x, const float* w9c, const float* bias, int B, i
 
 int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   const int cb = 32 * plan.cpl;
-  const int smem_bytes = kStages * (kBoxH * kBoxW * cb * 2) + 128;
+  static const int env_stages = [] { const char* e = getenv("SURGVID_DW_STAGES"); return e ? atoi(e) : 0; }();
+  static const int env_prefetch = [] { const char* e = getenv("SURGVID_DW_PREFETCH"); return e ? atoi(e) : 0; }();
+  const int stages = std::min(kMaxStages, std::max(2, env_stages > 0 ? env_stages : kStages));
+  const int prefetch = std::min(stages - 1, std::max(1, env_prefetch > 0 ? env_prefetch : kPrefetch));
+  const int smem_bytes = stages * (kBoxH * kBoxW * cb * 2) + 128;
   static const int gelu_mode = [] { const char* e = getenv("SURGVID_DW_GELU"); return e ? atoi(e) : 2; }();
   typedef void (*KernFn)(const CUtensorMap, const DwParams);
   KernFn kern;
@@ -268,6 +274,7 @@ int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   DwParams p;
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tw = plan.tw;
+  p.stages = stages; p.prefetch = prefetch;
   p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / cb;
   const long long nt = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
   if (nt >= (1LL << 31)) return fail(SV_ERR_INVALID, "dwconv: more than 2^31 tiles");
