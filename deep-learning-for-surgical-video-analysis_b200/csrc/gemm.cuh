@@ -35,6 +35,7 @@ struct GemmParams {
   int pair;         // 1: 2-CTA clusters; num_tiles counts 256-row pair tiles
   int prefetch;     // k-blocks of the A operand requested into L2 ahead of the shared-memory ring (0 = off)
   int kb_split;     // k-blocks served by the first A segment (all of them without a second segment)
+  int tma_out;      // 1: bf16 result without residual is written with 2-D TMA stores from a swizzled staging tile
   int act;
   int out_fp32;
   const float* bias;
@@ -48,6 +49,7 @@ struct GemmPlan {
   CUtensorMap tmap_a;
   CUtensorMap tmap_a2;   // second A segment (copy of tmap_a when unused)
   CUtensorMap tmap_w;
+  CUtensorMap tmap_out;  // bf16 result without residual: 2-D TMA store map (copy of tmap_a otherwise)
   GemmParams p;
   int grid = 0;
   size_t smem_bytes = 0;
@@ -57,6 +59,6 @@ struct GemmPlan {
 int gemm_plan(const GemmDesc& d, GemmPlan* plan);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 // pick the UMMA N for a problem (exposed for tests)
-int gemm_pick_block_n(int M, int N, int K, int num_sms);
+int gemm_pick_block_n(int M, int N, int K, int num_sms, int step = 16);
 
 }  // namespace sv

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "gemm.cuh"
@@ -49,7 +50,7 @@ constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
 template <int ACT, bool OUT_F32, bool RESID, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                         const __grid_constant__ CUtensorMap tmap_w, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -74,6 +75,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_a2);
     ptx::prefetch_tensormap(&tmap_w);
+    if constexpr (!OUT_F32 && !RESID && !PAIR) ptx::prefetch_tensormap(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -187,6 +189,94 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ------------------------------------------------------------------ epilogue warps
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // 0: even 32-column chunks, 1: odd chunks
+    bool done = false;
+    if constexpr (!OUT_F32 && !RESID && !PAIR) {
+      if (p.tma_out) {
+      done = true;
+      // bf16 result, no residual (fc1, q, kv, sr, adapter, flow and head projections): thread = accumulator row all the way.
+      // bias / activation / bf16 pack in registers, 64 bytes per row into a per-warp staging tile in the 64B-swizzled layout of a
+      // 2-D TMA store (box 32 columns x 32 rows; ragged M / N edges are clipped by the tensor map) — no transposition through
+      // shared memory and no per-thread global stores.  (ncu, round 2: the transposing epilogue ran the L1TEX LSU data pipe at
+      // 72-75 % on these GEMMs — 81 shared/global wavefronts per 32x32 block against 24 here.)
+      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 4096;   // two 2 KB buffers, 1 KB aligned
+      float* bias_s = bias_smem + (warp - 2) * 256;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      uint32_t n_store = 0;   // stores issued by this warp so far (lane 0's bulk groups)
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+        const int m0 = (tile / p.num_n_tiles) * kBlockM;
+        const int n0 = (tile % p.num_n_tiles) * p.block_n;
+        const int n_valid = min(p.block_n, p.N - n0);
+        const int nchunks = (n_valid + 31) >> 5;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = i * 128 + lane * 4;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && c < n_valid) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
+          *reinterpret_cast<float4*>(bias_s + c) = b;
+        }
+        __syncwarp();
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t r_a[32], r_b[32];
+        if (half < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(half * 32), r_a);
+        auto emit = [&](const uint32_t (&r)[32], int c) {
+          uint8_t* sb = sbase + (n_store & 1u) * 2048;
+          if (n_store >= 2u) {   // the store issued from this buffer two chunks ago has finished reading it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
+            float v0 = __uint_as_float(r[i]) + b4.x, v1 = __uint_as_float(r[i + 1]) + b4.y, v2 = __uint_as_float(r[i + 2]) + b4.z,
+                  v3 = __uint_as_float(r[i + 3]) + b4.w;
+            if constexpr (ACT == ACT_GELU) {
+              f32x2 lo = f2_pack(v0, v1), hi = f2_pack(v2, v3);
+              f2_gelu_erf_poly_x2(lo, hi);
+              f2_unpack(lo, v0, v1);
+              f2_unpack(hi, v2, v3);
+            } else if constexpr (ACT == ACT_RELU) {
+              v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+            }
+            w[i >> 1] = pack_bf16x2(v0, v1);
+            w[(i >> 1) + 1] = pack_bf16x2(v2, v3);
+          }
+          const int x = (lane >> 1) & 3;   // 64B swizzle: 16-byte chunk j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(sb + lane * 64 + ((j ^ x) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)),
+                         "r"(ptx::smem_u32(sb)), "r"(n0 + c * 32), "r"(m0 + quarter * 32)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++n_store;
+        };
+        for (int c = half; c < nchunks; c += 4) {
+          ptx::tmem_ld_wait();
+          if (c + 2 < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 2) * 32), r_b);
+          emit(r_a, c);
+          if (c + 2 >= nchunks) break;
+          ptx::tmem_ld_wait();
+          if (c + 4 < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>((c + 4) * 32), r_a);
+          emit(r_b, c + 2);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
+      }
+    }
+    if (!done) {
     float* stg = staging + (warp - 2) * (32 * kStageLd);
     float* bias_s = bias_smem + (warp - 2) * 256;
     const int sub_row = lane >> 3;  // 4 rows per warp instruction
@@ -259,6 +349,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    }
   }
 
   ptx::tc_fence_before();
@@ -311,7 +402,7 @@ int encode_operand_map(CUtensorMap* map, const bf16* base, int64_t rows, int64_t
 
 }  // namespace
 
-int gemm_pick_block_n(int M, int N, int K, int num_sms) {
+int gemm_pick_block_n(int M, int N, int K, int num_sms, int step) {
   // Candidates are legal UMMA N for M=128 (multiples of 16, <= 256).  Model: time ~ waves * (per-tile cost),
   // per-tile cost ~ fixed epilogue/pipeline overhead + N_tile * (k-blocks + epilogue share).
   // Per-tile cycle model (per SM): the slowest of
@@ -319,12 +410,14 @@ int gemm_pick_block_n(int M, int N, int K, int num_sms) {
   //   operand staging  (128 + c) * 128 bytes per k-block over ~48 B/cycle/SM of L2->SM bandwidth (A is re-read once per n-tile),
   //   epilogue         ~6 cycles per accumulator column for the warp's 32-row slab + fixed latency,
   // times the number of waves of the persistent grid.
-  const int n_pad = round_up(N, 16);
+  // step = 32 when the result leaves through 32-column TMA store boxes: a tile's column range must then end on a multiple of 32 or
+  // at the edge of the tensor (where the box is clipped), never in the middle of a neighbouring tile
+  const int n_pad = round_up(N, step);
   const int m_tiles = ceil_div(M, kBlockM);
   const int kb = ceil_div(K, kBlockK);
-  int best = 16;
   double best_cost = 1e30;
-  for (int c = 256; c >= 16; c -= 16) {
+  int best = step;
+  for (int c = 256; c >= step; c -= step) {
     if (c > n_pad) continue;
     const int n_tiles = ceil_div(N, c);
     const long long tiles = static_cast<long long>(m_tiles) * n_tiles;
@@ -353,7 +446,10 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   SV_CHECK(sms > 0, "no CUDA device");
   GemmParams& p = plan->p;
   p.M = d.M; p.N = d.N; p.K = d.K;
-  p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms);
+  p.pair = d.pair > 0 ? 1 : 0;
+  static const int tma_out_env = getenv("SURGVID_GEMM_TMA_OUT") ? atoi(getenv("SURGVID_GEMM_TMA_OUT")) : 1;   // A/B switch
+  p.tma_out = (!d.out_fp32 && d.residual == nullptr && !p.pair && tma_out_env) ? 1 : 0;
+  p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, p.tma_out ? 32 : 16);
   const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
   // CTA-pair mode pays off when operand staging (L2 -> smem) dominates: deep K and enough 256-row tiles to fill the machine
   // Measured on B200 (profiles/r01/gemm_pair_vs_single.log): at this path's shapes the pair mode is 5-20 % SLOWER than single-CTA
@@ -380,12 +476,26 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   if (d.K2 > 0) SV_TRY(encode_operand_map(&plan->tmap_a2, d.A2, d.M, d.K2, d.lda2, kBlockM));
   else plan->tmap_a2 = plan->tmap_a;
   SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, b_rows));
+  if (p.tma_out) {
+    // bf16 result without residual leaves through 2-D TMA stores: box = 32 columns x 32 rows, 64-byte swizzle
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d.N), static_cast<cuuint64_t>(d.M)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d.ldc) * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(gemm out) failed, CUresult " + std::to_string(static_cast<int>(r)));
+  } else {
+    plan->tmap_out = plan->tmap_a;
+  }
   return SV_OK;
 }
 
 namespace {
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
 
 template <int ACT, bool PAIR>
 GemmKernelFn pick_kernel(int out_fp32, bool resid) {
@@ -427,11 +537,11 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.p);
     if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaLaunchKernelEx(gemm pair): ") + cudaGetErrorString(e));
     return SV_OK;
   }
-  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.p);
+  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.p);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 

@@ -5,16 +5,20 @@ rows = list(csv.reader(open(sys.argv[1], errors="replace")))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 names, units, data = rows[hdr], rows[hdr + 1], rows[hdr + 2:]
 want = [
-    ("dur_us", r"gpu__time_duration\.sum$"),
-    ("dram_rd_MB", r"dram__bytes_read\.sum$"), ("dram_wr_MB", r"dram__bytes_write\.sum$"),
-    ("dram_pct", r"gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$"),
-    ("l2_pct", r"lts__throughput\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("dur_us", r"^gpu__time_duration\.sum$"),
+    ("dram_rd_MB", r"^dram__bytes_read\.sum$"), ("dram_wr_MB", r"^dram__bytes_write\.sum$"),
+    ("dram_pct", r"^gpu__dram_throughput\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("l2_pct", r"^lts__throughput\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("l2_to_sm_MB", r"^l1tex__m_xbar2l1tex_read_bytes\.sum$"),
     ("l2_hit_pct", r"lts__t_sector_hit_rate\.pct$"),
     ("sm_pct", r"sm__throughput\.avg\.pct_of_peak_sustained_elapsed$"),
-    ("tensor_pct", r"sm__pipe_tensor_cycles_active.*pct|sm__inst_executed_pipe_tensor.*pct|sm__pipe_tensor_op.*pct"),
-    ("uma_pct", r"sm__inst_executed_pipe_uma.*pct"),
-    ("fma_pct", r"sm__inst_executed_pipe_fma(?!heavy|lite).*pct|sm__pipe_fma_cycles_active.*pct"),
-    ("xu_pct", r"sm__inst_executed_pipe_xu.*pct"),
+    ("tensor_pct", r"^sm__pipe_tensor_cycles_active\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("tc_pct", r"^sm__pipe_tc_cycles_active\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("lsu_wavefront_pct", r"^l1tex__data_pipe_lsu_wavefronts\.avg\.pct_of_peak_sustained_elapsed$"),
+    
+    ("fma_pct", r"^sm__pipe_fma_cycles_active\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("alu_pct", r"^sm__pipe_alu_cycles_active\.avg\.pct_of_peak_sustained_elapsed$"),
+    ("xu_pct", r"^sm__inst_executed_pipe_xu\.avg\.pct_of_peak_sustained_active$"),
     ("issue_pct", r"smsp__issue_active\.avg\.pct"), ("ipc", r"sm__inst_executed\.avg\.per_cycle_elapsed$"),
     ("warps_active_pct", r"sm__warps_active\.avg\.pct_of_peak_sustained_active$"),
     ("regs", r"launch__registers_per_thread$"), ("smem_dyn_KB", r"launch__shared_mem_per_block_dynamic$"),
@@ -36,7 +40,11 @@ for r in data:
         if i is None or r[i] in ("", "n/a"):
             d[key] = ""
             continue
-        v = float(r[i].replace(",", ""))
+        try:
+            v = float(r[i].replace(",", ""))
+        except ValueError:
+            d[key] = ""
+            continue
         u = units[i]
         if key.endswith("_MB"):
             v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
