@@ -49,7 +49,8 @@ struct GemmPlan {
   CUtensorMap tmap_a;
   CUtensorMap tmap_a2;   // second A segment (copy of tmap_a when unused)
   CUtensorMap tmap_w;
-  CUtensorMap tmap_out;  // bf16 result without residual: 2-D TMA store map (copy of tmap_a otherwise)
+  CUtensorMap tmap_out;  // TMA epilogue: 2-D store map of the result (copy of tmap_a when unused)
+  CUtensorMap tmap_res;  // TMA epilogue: 2-D load map of the fp32 residual (copy of tmap_a when unused)
   GemmParams p;
   int grid = 0;
   size_t smem_bytes = 0;

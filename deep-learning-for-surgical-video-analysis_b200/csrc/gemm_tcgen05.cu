@@ -50,13 +50,15 @@ constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
 template <int ACT, bool OUT_F32, bool RESID, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
-                         const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out, const GemmParams p) {
+                         const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_out,
+                         const __grid_constant__ CUtensorMap tmap_res, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(8) uint64_t res_full[kEpiWarps][2];   // fp32 TMA epilogue: residual chunk landed in the warp's staging buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -75,13 +77,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_a2);
     ptx::prefetch_tensormap(&tmap_w);
-    if constexpr (!OUT_F32 && !RESID && !PAIR) ptx::prefetch_tensormap(&tmap_out);
+    if constexpr ((OUT_F32 || !RESID) && !PAIR) ptx::prefetch_tensormap(&tmap_out);
+    if constexpr (OUT_F32 && RESID && !PAIR) ptx::prefetch_tensormap(&tmap_res);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int w = 0; w < kEpiWarps; ++w) {
+        ptx::mbar_init(&res_full[w][0], 1);
+        ptx::mbar_init(&res_full[w][1], 1);
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -276,6 +283,121 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
       }
     }
+    if constexpr (OUT_F32 && !PAIR) {
+      if (p.tma_out) {
+      done = true;
+      // fp32 result, optionally read-modify-write of an fp32 residual (proj / fc2 / shared: x += ...): thread = accumulator row; the
+      // residual arrives by 2-D TMA loads (box 16 columns x 32 rows, 64-byte swizzle) into a 2-deep per-warp ring, issued while the
+      // tile's MMAs are still running; the row is updated in place in shared memory and leaves through a TMA store of the same box.
+      // No transposition, no per-thread global loads/stores, no long-scoreboard stalls on the residual stream.
+      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 4096;   // two 2 KB buffers, 1 KB aligned
+      float* bias_s = bias_smem + (warp - 2) * 256;
+      uint64_t* rbar = res_full[warp - 2];
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      uint32_t n_chunk = 0;   // chunks this warp has processed so far: buffer = n_chunk & 1, barrier parity = (n_chunk >> 1) & 1
+      const int x = (lane >> 1) & 3;   // 64B swizzle: 16-byte piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+        const int m0 = (tile / p.num_n_tiles) * kBlockM;
+        const int n0 = (tile % p.num_n_tiles) * p.block_n;
+        const int n_valid = min(p.block_n, p.N - n0);
+        const int nch16 = (n_valid + 15) >> 4;
+        const int my_chunks = (nch16 - half + 1) >> 1;          // this warp takes 16-column chunks half, half + 2, ...
+        auto load_res = [&](int k) {                             // k-th chunk of this warp in this tile -> ring slot (n_chunk + k) & 1
+          if (lane == 0) {
+            const uint32_t slot = (n_chunk + static_cast<uint32_t>(k)) & 1u;
+            ptx::mbar_arrive_expect_tx(&rbar[slot], 2048u);
+            ptx::tma_load_2d(sbase + slot * 2048, &tmap_res, &rbar[slot], n0 + (half + 2 * k) * 16, m0 + quarter * 32);
+          }
+        };
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int c = i * 128 + lane * 4;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && c < n_valid) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
+          *reinterpret_cast<float4*>(bias_s + c) = b;
+        }
+        if constexpr (RESID) {
+          // both ring slots are free here: every store of the previous tile was waited for (wait_group.read) before its slot was
+          // refilled or, for the last two, right below at the end of the tile
+          if (my_chunks > 0) load_res(0);
+          if (my_chunks > 1) load_res(1);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t r_a[16], r_b[16];
+        if (my_chunks > 0) ptx::tmem_ld_x16(t_row + static_cast<uint32_t>(half * 16), r_a);
+        auto emit = [&](const uint32_t (&r)[16], int k) {
+          const int c16 = half + 2 * k;
+          const uint32_t slot = n_chunk & 1u;
+          uint8_t* sb = sbase + slot * 2048;
+          float* rowp = reinterpret_cast<float*>(sb + lane * 64);
+          if constexpr (RESID) {
+            ptx::mbar_wait(&rbar[slot], (n_chunk >> 1) & 1u);
+          } else {
+            if (n_chunk >= 2u) {   // the store issued from this slot two chunks ago has finished reading it
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              __syncwarp();
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4* pp = reinterpret_cast<float4*>(rowp + ((j ^ x) << 2));
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c16 * 16 + j * 4);
+            float4 v = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
+                                   __uint_as_float(r[4 * j + 3]) + b4.w);
+            if constexpr (ACT == ACT_GELU) {
+              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+            } else if constexpr (ACT == ACT_RELU) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            if constexpr (RESID) {
+              const float4 q = *pp;
+              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+            }
+            *pp = v;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)),
+                         "r"(ptx::smem_u32(sb)), "r"(n0 + c16 * 16), "r"(m0 + quarter * 32)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if constexpr (RESID) {
+              if (k + 2 < my_chunks) {   // refill this slot with the residual of the chunk after next once the store has read it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                const uint32_t s2 = slot;
+                ptx::mbar_arrive_expect_tx(&rbar[s2], 2048u);
+                ptx::tma_load_2d(sb, &tmap_res, &rbar[s2], n0 + (c16 + 4) * 16, m0 + quarter * 32);
+              }
+            }
+          }
+          ++n_chunk;
+        };
+        for (int k = 0; k < my_chunks; k += 2) {
+          ptx::tmem_ld_wait();
+          if (k + 1 < my_chunks) ptx::tmem_ld_x16(t_row + static_cast<uint32_t>((half + 2 * (k + 1)) * 16), r_b);
+          emit(r_a, k);
+          if (k + 1 >= my_chunks) break;
+          ptx::tmem_ld_wait();
+          if (k + 2 < my_chunks) ptx::tmem_ld_x16(t_row + static_cast<uint32_t>((half + 2 * (k + 2)) * 16), r_a);
+          emit(r_b, k + 1);
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          if constexpr (RESID) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // both slots free for the next tile's residual loads
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
+      }
+    }
     if (!done) {
     float* stg = staging + (warp - 2) * (32 * kStageLd);
     float* bias_s = bias_smem + (warp - 2) * 256;
@@ -448,8 +570,10 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.pair = d.pair > 0 ? 1 : 0;
   static const int tma_out_env = getenv("SURGVID_GEMM_TMA_OUT") ? atoi(getenv("SURGVID_GEMM_TMA_OUT")) : 1;   // A/B switch
-  p.tma_out = (!d.out_fp32 && d.residual == nullptr && !p.pair && tma_out_env) ? 1 : 0;
-  p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, p.tma_out ? 32 : 16);
+  // bf16 result without residual, or fp32 result with / without an fp32 residual (the bf16 + residual combination keeps the transposing epilogue)
+  p.tma_out = ((d.out_fp32 || d.residual == nullptr) && !p.pair && tma_out_env) ? 1 : 0;
+  if (p.tma_out && d.out_fp32 && ((d.ldc * 4) % 16 != 0 || (d.residual && (d.ldr * 4) % 16 != 0))) p.tma_out = 0;
+  p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, (p.tma_out && !d.out_fp32) ? 32 : 16);
   const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
   // CTA-pair mode pays off when operand staging (L2 -> smem) dominates: deep K and enough 256-row tiles to fill the machine
   // Measured on B200 (profiles/r01/gemm_pair_vs_single.log): at this path's shapes the pair mode is 5-20 % SLOWER than single-CTA
@@ -476,26 +600,32 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   if (d.K2 > 0) SV_TRY(encode_operand_map(&plan->tmap_a2, d.A2, d.M, d.K2, d.lda2, kBlockM));
   else plan->tmap_a2 = plan->tmap_a;
   SV_TRY(encode_operand_map(&plan->tmap_w, d.W, d.N, d.K, d.ldw, b_rows));
+  plan->tmap_out = plan->tmap_a;
+  plan->tmap_res = plan->tmap_a;
   if (p.tma_out) {
-    // bf16 result without residual leaves through 2-D TMA stores: box = 32 columns x 32 rows, 64-byte swizzle
+    // bf16: box = 32 columns x 32 rows; fp32: box = 16 columns x 32 rows; 64 bytes per box row, 64-byte swizzle
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
-    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d.N), static_cast<cuuint64_t>(d.M)};
-    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(d.ldc) * 2};
-    cuuint32_t box[2] = {32, 32};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(&plan->tmap_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(gemm out) failed, CUresult " + std::to_string(static_cast<int>(r)));
-  } else {
-    plan->tmap_out = plan->tmap_a;
+    auto enc = [&](CUtensorMap* m, const void* base, int64_t ld) -> int {
+      const int es = d.out_fp32 ? 4 : 2;
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(d.N), static_cast<cuuint64_t>(d.M)};
+      cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * es};
+      cuuint32_t box[2] = {static_cast<cuuint32_t>(64 / es), 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = fn(m, d.out_fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(SV_ERR_CUDA, "cuTensorMapEncodeTiled(gemm out) failed, CUresult " + std::to_string(static_cast<int>(r)));
+      return SV_OK;
+    };
+    SV_TRY(enc(&plan->tmap_out, d.out, d.ldc));
+    if (d.residual) SV_TRY(enc(&plan->tmap_res, d.residual, d.ldr));
   }
   return SV_OK;
 }
 
 namespace {
 
-typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
 
 template <int ACT, bool PAIR>
 GemmKernelFn pick_kernel(int out_fp32, bool resid) {
@@ -537,11 +667,11 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.tmap_res, plan.p);
     if (e != cudaSuccess) return fail(SV_ERR_CUDA, std::string("cudaLaunchKernelEx(gemm pair): ") + cudaGetErrorString(e));
     return SV_OK;
   }
-  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.p);
+  fn<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(plan.tmap_a, plan.tmap_a2, plan.tmap_w, plan.tmap_out, plan.tmap_res, plan.p);
   return launch_status("gemm_bf16_tcgen05_kernel");
 }
 
