@@ -34,7 +34,12 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FRAMES_PER_VIDEO = 2300
-BATCH = 800  # throughput-optimal on B200; the reference driver uses 200 (generate_evp_LFB.py:36), see DESIGN.md for both
+# Frames per forward (= micro-batch).  The reference driver uses 200 (generate_evp_LFB.py:36).  Large batches amortise weight streams and
+# launches; the exact value is chosen so that the stage-3 GEMMs (M = 196 tokens x frames, 128-row tiles on 148 SMs) fill whole waves of
+# the persistent grid: 1150 frames = 11.90 waves (two equal batches of a 2 300-frame video), 1159 = 11.99 waves at every stage
+# (800 = 8.28 waves wasted 8 % of the last wave: measured 123.4 vs 120.8 ms per video on the same box).
+BATCH = 1150
+BATCH_JOB = 1159
 FLOPS_PER_FRAME_REF = 16.664e9  # reference graph @224^2 with flow
 FLOPS_PER_FRAME_REF_480 = 166.02e9  # @480x854
 
@@ -49,9 +54,9 @@ def parse():
     ap.add_argument("--hw", default="224x224", help="frame size HxW; 480x854 selects the native480 workload")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_VIDEO)
     ap.add_argument("--batch", type=int, default=None)
-    ap.add_argument("--pool", type=int, default=2400, help="cholec80x80: frames in the per-rank synthetic input pool the videos cycle through")
+    ap.add_argument("--pool", type=int, default=2318, help="cholec80x80: frames in the per-rank synthetic input pool the videos cycle through (rounded down to a multiple of --batch)")
     ap.add_argument("--videos", type=int, default=80, help="cholec80x80: use only the first N videos (tests)")
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("SURGVID_MICRO_BATCH", "800")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("SURGVID_MICRO_BATCH", "0")), help="frames per plan inside a forward (default: = --batch)")
     ap.add_argument("--fold-head", type=int, default=int(os.environ.get("SURGVID_FOLD_HEAD", "0")))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,7 +67,9 @@ def parse():
     if a.workload == "auto":
         a.workload = "native480" if (a.H, a.W) != (224, 224) else ("video2300" if a.gpus <= 1 else "cholec80x80")
     if a.batch is None:
-        a.batch = 64 if a.workload == "native480" else BATCH
+        a.batch = 64 if a.workload == "native480" else (BATCH_JOB if a.workload == "cholec80x80" else BATCH)
+    if a.micro_batch <= 0:
+        a.micro_batch = a.batch
     return a
 
 
@@ -499,7 +506,7 @@ def run_cholec80(ctx):
     B, P = a.batch, max(a.batch, (a.pool // a.batch) * a.batch)
     loads = [sum(lengths[v] for v in vs) for vs in assign]
     # Inputs: 184 578 frames are 295 GB as fp32 tensors, more than fits next to the workspace at N <= 2, so every rank keeps a POOL of P
-    # distinct synthetic frames resident (3.9 GB, >> L2) and its videos cycle through it; frame t of the rank's stream is pool row t % P.
+    # distinct synthetic frames resident (3.7 GB, >> L2) and its videos cycle through it; frame t of the rank's stream is pool row t % P.
     x, seg, flow = ctx.synth_device_frames(P, a.H, a.W, 1234 + rank)
     feats_d = torch.empty((R, 2048), dtype=torch.float32, device=dev)
     douts, o = [], 0
@@ -608,7 +615,7 @@ def run_cholec80(ctx):
     extra = {"frames_per_step": total, "videos": len(lengths), "lpt_frames_per_rank": loads, "lpt_imbalance": max(loads) / (total / world) - 1.0,
              "input_pool_frames_per_rank": P, "gather": f"page-locked shared-memory LFB array ({'pinned' if shared.pinned else 'NOT pinned'}), rows in video order",
              "gather_verified": ok,
-             "l2": "the 3.9 GB resident input pool and the 11 GB workspace are far larger than the 126 MB L2; no flush needed"}
+             "l2": "the 3.7 GB resident input pool and the 16 GB workspace are far larger than the 126 MB L2; no flush needed"}
     line = base_line(ctx, value, ms_total, nwarm, clocks, launches_all, e2e, roofline, cpu, classes, whole, extra)
     shared.unlink(), shared_lg.unlink()
     ctx.emit(line)

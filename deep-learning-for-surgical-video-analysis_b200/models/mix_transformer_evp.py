@@ -197,7 +197,9 @@ class MixVisionTransformerEVP(nn.Module):
         self.cross_attn_s4 = MotionGuidedCrossAttention(dim=embed_dims[3])
         # ---- native state (not parameters, not in state_dict)
         self.embedding_dim = self.head.embedding_dim
-        self.micro_batch = int(os.environ.get("SURGVID_MICRO_BATCH", "800"))
+        # frames per launch plan inside one forward call; 1159 frames x 196 stage-3 tokens = 11.99 full waves of 128-row GEMM tiles on
+        # 148 SMs (800 = 8.28 waves wasted 8 % of the last one); 16 GB of workspace at 224x224
+        self.micro_batch = int(os.environ.get("SURGVID_MICRO_BATCH", "1159"))
         self.fold_head = bool(int(os.environ.get("SURGVID_FOLD_HEAD", "0")))
         self._native = {}  # device index -> dict(handle, stamp, workspace)
 

@@ -1,19 +1,48 @@
 #!/bin/bash
-# Round-end evidence run: full GPU test suite, smoke, default bench (+reference arm), ncu launch list and GEMM DRAM traffic.
-mkdir -p gpurun_out
+# Round-end evidence run on ONE B200: full GPU test suite, smoke, default bench as the driver launches it (+ reference arm), batch
+# variants, the 80-video job on one GPU, the 480x854 line, MS-TCN, and ncu (launch list of one micro-batch + --set full of the GEMM).
+O=gpurun_out/r02; mkdir -p $O
 cd "$(dirname "$0")/.."
-run() { name=$1; shift; echo "=== $name" ; timeout "${TMO:-900}" "$@" > gpurun_out/$name.log 2>&1; rc=$?; echo "$name rc=$rc"; tail -n "${TAILN:-4}" gpurun_out/$name.log; return $rc; }
-run pytest_gpu python -m pytest tests -q -m gpu -x || exit 1
-run smoke python __graft_entry__.py smoke || exit 1
-echo "=== bench (defaults)"
-SURGVID_PROFILE_CSV=gpurun_out/profile_ops_final.csv timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "rc=$?"; tail -c 300 gpurun_out/bench_final.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "ref rc=$?"
-timeout 600 python bench.py --batch 200 --micro-batch 200 --no-cpu-baseline > gpurun_out/bench_batch200.json 2> gpurun_out/bench_batch200.err; echo "b200 rc=$?"
-timeout 600 python bench.py --fold-head 1 --no-cpu-baseline --no-e2e > gpurun_out/bench_foldhead.json 2> gpurun_out/bench_foldhead.err; echo "fold rc=$?"
-python scripts/mstcn_bench.py 2>&1 | tail -1 | tee gpurun_out/mstcn_bench.log
+run() { name=$1; shift; echo "=== $name" ; timeout "${TMO:-1200}" "$@" > $O/$name.log 2>&1; rc=$?; echo "$name rc=$rc"; tail -n "${TAILN:-3}" $O/$name.log | cut -c1-220; return $rc; }
+run pytest_gpu_final python -m pytest tests -q -m gpu -x -s || exit 1
+run smoke_final python __graft_entry__.py smoke || exit 1
+echo "=== bench (as the driver runs it)"
+SURGVID_PROFILE_CSV=$O/profile_ops_final.csv timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_final.json 2> $O/bench_final.err; echo "rc=$?"; tail -c 300 $O/bench_final.err
+timeout 600 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 > $O/bench_final_reference.json 2> /dev/null; echo "ref rc=$?"
+timeout 600 python bench.py --batch 200 --micro-batch 200 --no-cpu-baseline --no-e2e > $O/bench_final_batch200.json 2> /dev/null; echo "b200 rc=$?"
+timeout 600 python bench.py --batch 1150 --micro-batch 1150 --no-cpu-baseline --no-e2e > $O/bench_final_batch1150.json 2> /dev/null; echo "b1150 rc=$?"
+timeout 600 python bench.py --fold-head 1 --no-cpu-baseline --no-e2e > $O/bench_final_foldhead.json 2> /dev/null; echo "fold rc=$?"
+timeout 900 python bench.py --hw 480x854 --batch 64 --steps 10 --warmup 3 > $O/bench_final_480.json 2> /dev/null; echo "480 rc=$?"
+timeout 900 python bench.py --workload cholec80x80 --steps 1 --warmup 1 --no-cpu-baseline > $O/bench_final_job_n1.json 2> /dev/null; echo "job n1 rc=$?"
+REPS=20 python scripts/mstcn_bench.py 2>&1 | tail -1 | tee $O/mstcn_bench_final.log
+python - <<'PY'
+import json
+for f in ['bench_final','bench_final_batch200','bench_final_batch1150','bench_final_foldhead','bench_final_480','bench_final_job_n1','bench_final_reference']:
+    try:
+        d=json.loads(open(f'gpurun_out/r02/{f}.json').read().strip().splitlines()[-1])
+        k=d.get('kernel_classes') or {}
+        print(f, round(d['value'],1), round(d['ms_per_step'],2), d.get('e2e') and round(d['e2e']['value']), {n:round(v['ms'],2) for n,v in k.items() if v['ms']>1}, d.get('roofline') and round(d['roofline']['frac'],3), d.get('clocks') and d['clocks']['sm_mhz'])
+    except Exception as e: print(f, 'ERR', e)
+PY
 if [ "${NCU:-1}" = "1" ]; then
+NCUB="ncu --clock-control none"
+export SURGVID_NCU_RANGE=1
 CMD="python bench.py --frames 800 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-$CMD > gpurun_out/ncu_plain.log 2>&1 && \
-timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 1540 -c 365 --csv --log-file gpurun_out/launches_final.csv $CMD > gpurun_out/ncu_final.log 2>&1
-echo "ncu rc=$?"; wc -l gpurun_out/launches_final.csv
+$CMD > $O/ncu_plain_bench.log 2>&1 && $NCUB --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file $O/launches_r02_final_batch800.csv $CMD > $O/ncu_launches.log 2>&1
+echo "launch list rc=$?"
+unset SURGVID_NCU_RANGE
+for sh in 10 11 12 0; do
+  CMD="python scripts/gemm_bench.py $sh"
+  REPS=1 $CMD > $O/ncu_plain_gemm_$sh.log 2>&1 && REPS=1 $NCUB --set full --import-source on -k regex:gemm_bf16_tcgen05 -s 2 -c 1 -o $O/ncu_gemm_final_shape$sh -f $CMD > $O/ncu_gemm_$sh.log 2>&1
+  echo "gemm shape $sh rc=$?"
+  ncu -i $O/ncu_gemm_final_shape$sh.ncu-rep --page raw --csv > $O/ncu_gemm_final_shape${sh}_raw.csv 2>/dev/null
+done
+rm -f $O/ncu_gemm_final_shape11.ncu-rep $O/ncu_gemm_final_shape12.ncu-rep $O/ncu_gemm_final_shape0.ncu-rep
+CMD="python scripts/op_bench.py attn"
+REPS=1 $CMD > $O/ncu_plain_attn.log 2>&1 && REPS=1 $NCUB --set full -k regex:attention -c 15 -o $O/ncu_attn_tmp -f $CMD > $O/ncu_attn.log 2>&1
+ncu -i $O/ncu_attn_tmp.ncu-rep --page raw --csv > $O/ncu_attn_final_raw.csv 2>/dev/null; rm -f $O/ncu_attn_tmp.ncu-rep
+CMD="python scripts/op_bench.py dwconv"
+REPS=1 $CMD > $O/ncu_plain_dw.log 2>&1 && REPS=1 $NCUB --set full -k regex:dwconv3x3 -c 6 -o $O/ncu_dw_tmp -f $CMD > $O/ncu_dw.log 2>&1
+ncu -i $O/ncu_dw_tmp.ncu-rep --page raw --csv > $O/ncu_dwconv_final_raw.csv 2>/dev/null; rm -f $O/ncu_dw_tmp.ncu-rep
+du -sh $O
 fi
