@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsurgvid.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dwconv_tma.cu", "stem.cu", "mixffn.cu", "mstcn.cu", "evp.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dwconv_tma.cu", "stem.cu", "mixffn.cu", "mstcn.cu", "trans_head.cu", "evp.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 SV_OK = 0
@@ -28,12 +28,18 @@ EXPORTED_SYMBOLS = [
     "sv_op_gemm_bf16", "sv_op_layernorm", "sv_op_im2col", "sv_op_dwconv3x3_gelu", "sv_op_attention", "sv_op_gauss5x5",
     "sv_op_bilinear_tokens", "sv_op_token_mean", "sv_op_stem_conv", "sv_op_mixffn_fc2", "sv_op_gemm_bf16_cat",
     "sv_prep_create", "sv_prep_destroy", "sv_prep_workspace_bytes", "sv_prep_images", "sv_prep_flow",
+    "sv_trans_create", "sv_trans_destroy", "sv_trans_set_tensor", "sv_trans_pack_weights", "sv_trans_forward",
 ]
 
 
 class EvpCfg(Structure):
     _fields_ = [("embed_dims", c_int32 * 4), ("num_heads", c_int32 * 4), ("depths", c_int32 * 4), ("sr_ratios", c_int32 * 4),
                 ("mlp_ratio", c_int32), ("embedding_dim", c_int32), ("fold_head", c_int32)]
+
+
+class TransCfg(Structure):
+    _fields_ = [("d_model", c_int32), ("d_ff", c_int32), ("d_k", c_int32), ("d_v", c_int32), ("n_layers", c_int32), ("n_heads", c_int32),
+                ("len_q", c_int32)]
 
 
 class MstcnCfg(Structure):
@@ -128,6 +134,11 @@ def _declare(lib):
     lib.sv_op_token_mean.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.sv_op_mixffn_fc2.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32,
                                      c_int32, c_int32, c_int32, c_void_p]
+    lib.sv_trans_create.argtypes = [POINTER(TransCfg), POINTER(c_void_p)]
+    lib.sv_trans_destroy.argtypes = [c_void_p]
+    lib.sv_trans_set_tensor.argtypes = [c_void_p, c_char_p, c_void_p, i64p, c_int32]
+    lib.sv_trans_pack_weights.argtypes = [c_void_p]
+    lib.sv_trans_forward.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, i64p, c_int32, c_void_p, c_void_p]
     lib.sv_prep_create.argtypes = [c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, f32p, f32p, POINTER(c_void_p)]
     lib.sv_prep_destroy.argtypes = [c_void_p]
     lib.sv_prep_workspace_bytes.argtypes = [c_void_p, c_int32]

@@ -36,7 +36,7 @@ extern "C" {
 #define SV_ERR_STATE 3       /* call order violated (e.g. forward before pack_weights) */
 #define SV_ERR_UNSUPPORTED 4 /* configuration outside what the kernels implement */
 
-#define SV_ABI_VERSION 1
+#define SV_ABI_VERSION 2
 #define SV_PROFILE_CLASSES 9
 
 const char* sv_last_error(void);
@@ -221,6 +221,34 @@ int sv_op_mixffn_fc2(const uint16_t* h1, const float* w10c, const uint16_t* Wcat
 
 /* mean over `tokens` consecutive rows of fp32 [B*tokens, C] -> [B, C] (AdaptiveAvgPool2d(1), segformer_head.py:167). */
 int sv_op_token_mean(const float* x, int32_t B, int32_t tokens, int32_t C, float* out, void* stream);
+
+/* ---- Trans-SVNet head: the inner module of adapter_transformer.Transformer —
+ * `self.transformer = Transformer2_3_1(d_model=out_features, d_ff=mstcn_f_maps, d_k=d_v=min(64, mstcn_f_maps), n_layers=1, n_heads=4,
+ * len_q=sequence_length)` (adapter_transformer.py:317-325) called as `self.transformer(inputs, feas)` (:348) — fused with the window
+ * construction of Transformer.original_forward (:335-344): the kernel reads the MS-TCN logits and the decoder query directly.
+ * The source of Transformer2_3_1 is absent from the reference tree; the arithmetic is the published upstream architecture restated in
+ * oracle/trans_head_oracle.py (PARITY UNPINNED).  state_dict keys expected by sv_trans_set_tensor:
+ *   {encoder.layers.0.enc_self_attn, decoder.layers.0.dec_enc_attn}.{W_Q,W_K,W_V,fc}.{weight[,bias]}, .layer_norm.{weight,bias},
+ *   {encoder,decoder}.layers.0.pos_ffn.{fc1,fc2}.{weight[,bias]}, .layer_norm.{weight,bias}   (missing biases = 0). */
+typedef struct sv_trans_cfg {
+  int32_t d_model;   /* out_features (14) */
+  int32_t d_ff;      /* mstcn_f_maps (32) */
+  int32_t d_k, d_v;  /* min(64, mstcn_f_maps); 32 supported */
+  int32_t n_layers;  /* 1 */
+  int32_t n_heads;   /* 4 */
+  int32_t len_q;     /* sequence_length (30), <= 32 */
+} sv_trans_cfg;
+typedef struct sv_trans sv_trans_handle;
+int sv_trans_create(const sv_trans_cfg* cfg, sv_trans_handle** out);
+int sv_trans_destroy(sv_trans_handle* h);
+int sv_trans_set_tensor(sv_trans_handle* h, const char* name, const float* host_data, const int64_t* shape, int32_t ndim);
+int sv_trans_pack_weights(sv_trans_handle* h);
+/* logits: fp32 channel-major [d_model][ldx] = the LAST stage of sv_mstcn_forward's output for the concatenated videos
+ * (x of Transformer.original_forward, adapter_transformer.py:329-330); query: fp32 [T, d_model] = tanh(fc(LFB)) (sv_mstcn_forward_query);
+ * video_offsets: host int64 [n_videos + 1]; out: fp32 [T, d_model] = transformer(inputs, feas).squeeze(1).  Windows are zero-padded on
+ * the left and never cross a video boundary. */
+int sv_trans_forward(sv_trans_handle* h, const float* logits, int64_t ldx, const float* query, const int64_t* video_offsets,
+                     int32_t n_videos, float* out, void* stream);
 
 /* ---- on-GPU input transforms: the reference's per-frame dataset transforms, applied to device copies of
  * the raw uint8 frames / float32 RAFT flow instead of on the CPU inside CholecFlowDataset.__getitem__ (data_process.py:409-483).

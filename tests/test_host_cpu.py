@@ -92,7 +92,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _native.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.sv_abi_version() == 1
+    assert lib.sv_abi_version() == 2
     # argument validation works without a device and reports through sv_last_error
     assert lib.sv_evp_create(None, None) != 0
     assert b"null" in lib.sv_last_error()
@@ -159,3 +159,21 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), list)
     if not __import__("torch").cuda.is_available():
         assert os.sched_getaffinity(0) == before
+
+
+def test_trans_head_holder_keys_and_no_cpu_path():
+    """adapter_transformer.Transformer's constructor arguments (adapter_transformer.py:290-325); the inner module's source is absent
+    from the reference, so its parameter names are this package's (documented as parity-unpinned)."""
+    import pytest
+    import torch
+    from surgvid_b200.trans_head import Transformer
+    head = Transformer(32, 2048, 14, 30)
+    keys = set(head.state_dict())
+    assert "fc.weight" in keys and head.fc.weight.shape == (14, 2048) and head.fc.bias is None
+    for blk in ("transformer.encoder.layers.0.enc_self_attn", "transformer.decoder.layers.0.dec_enc_attn"):
+        for p in ("W_Q", "W_K", "W_V", "fc"):
+            assert f"{blk}.{p}.weight" in keys
+        assert head.state_dict()[f"{blk}.W_Q.weight"].shape == (4 * 32, 14)
+    assert head.transformer.d_k == 32 and head.transformer.d_ff == 32 and head.transformer.len_q == 30
+    with pytest.raises(RuntimeError):
+        head.eval().transformer.forward_fused(torch.zeros(14, 5), torch.zeros(5, 14), [5])
