@@ -8,7 +8,8 @@
 // residual + LayerNorm, position-wise FFN with ReLU, residual + LayerNorm), one decoder layer whose single query cross-attends the
 // encoder output (same blocks).  fp32 throughout (d_model = 14: nothing here is tensor-core shaped).
 //
-// One persistent CTA (128 threads = 4 warps = 4 heads) walks frames t; all weights (86 KB, d_model padded to 16) stay in shared memory.
+// One persistent CTA = two groups of 128 threads (4 warps = 4 heads each); every group walks its own frames t with its own Q/K/V tiles
+// and named barriers, and both share the weights (86 KB, d_model padded to 16) in shared memory.
 #include <string.h>
 
 #include <map>
@@ -54,28 +55,33 @@ __device__ __forceinline__ void layer_norm_inplace(float (&v)[kDP], int D, const
   for (int c = 0; c < kDP; ++c) v[c] = (c < D) ? (v[c] - m) * r * g[c] + b[c] : 0.f;
 }
 
-__global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict__ logits, int64_t ldx, const float* __restrict__ query,
+constexpr int kGroups = 2;                                       // 128-thread groups per CTA
+constexpr int kGroupFloats = 3 * kLMax * kLdS + 3 * kLMax * kDP + kDP;   // per-group tiles
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+__global__ void __launch_bounds__(128 * kGroups) trans_head_kernel(const float* __restrict__ logits, int64_t ldx, const float* __restrict__ query,
                                                          const int64_t* __restrict__ offsets, int64_t T, const float* __restrict__ blob,
                                                          float* __restrict__ out, const TransParams p) {
   extern __shared__ __align__(16) float sm[];
   float* Wb = sm;                              // kBlobSize
-  float* Qs = Wb + kBlobSize;                  // [kLMax][kLdS]  Q, then the attention context
+  const int grp = threadIdx.x >> 7;
+  float* Qs = Wb + kBlobSize + grp * kGroupFloats;   // [kLMax][kLdS]  Q, then the attention context
   float* Ks = Qs + kLMax * kLdS;
   float* Vs = Ks + kLMax * kLdS;
   float* Xs = Vs + kLMax * kLdS;               // [kLMax][kDP]  window
   float* Ys = Xs + kLMax * kDP;                // [kLMax][kDP]
   float* Es = Ys + kLMax * kDP;                // [kLMax][kDP]  encoder output
   float* qv = Es + kLMax * kDP;                // [kDP] decoder query
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;
   const int D = p.D, L = p.L, FF = p.FF;
-  for (int i = tid; i < kBlobSize / 4; i += 128) reinterpret_cast<float4*>(Wb)[i] = __ldg(reinterpret_cast<const float4*>(blob) + i);
+  for (int i = threadIdx.x; i < kBlobSize / 4; i += 128 * kGroups) reinterpret_cast<float4*>(Wb)[i] = __ldg(reinterpret_cast<const float4*>(blob) + i);
   const float* EA = Wb;
   const float* EF = EA + kAttnSize;
   const float* DA = EF + kFfnSize;
   const float* DF = DA + kAttnSize;
   __syncthreads();
 
-  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * kGroups + grp; t < T; t += static_cast<int64_t>(gridDim.x) * kGroups) {
     // first frame of t's video (zero left padding of the window never crosses a video boundary, adapter_transformer.py:336-341)
     int lo = 0, hi = p.n_videos;
     while (hi - lo > 1) {
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
       Xs[idx] = (c < D && src >= start) ? __ldg(logits + static_cast<int64_t>(c) * ldx + src) : 0.f;
     }
     if (tid < kDP) qv[tid] = tid < D ? __ldg(query + t * D + tid) : 0.f;
-    __syncthreads();
+    group_sync(grp);
     // ---- (2) encoder Q, K, V: thread = one of the 128 projection columns
     {
       float wq[kDP], wk[kDP], wv[kDP];
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
         Qs[i * kLdS + tid] = q; Ks[i * kLdS + tid] = k; Vs[i * kLdS + tid] = v;
       }
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- (3) self-attention: warp = head, lane = query row
     if (lane < L) {
       float q[kDK];
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
 #pragma unroll
       for (int d = 0; d < kDK; ++d) Qs[lane * kLdS + warp * kDK + d] = ctx[d];   // only this lane ever read this Q row
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- (4) output projection + residual: warp = group of 4 channels, lane = row
     if (lane < L) {
       float acc[4];
@@ -155,7 +161,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
 #pragma unroll
       for (int u = 0; u < 4; ++u) Ys[lane * kDP + warp * 4 + u] = acc[u];
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- LayerNorm, FFN, LayerNorm per row (warp 0, lane = row)
     if (warp == 0 && lane < L) {
       float y[kDP];
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
 #pragma unroll
       for (int c = 0; c < kDP; ++c) Es[lane * kDP + c] = o[c];
     }
-    __syncthreads();
+    group_sync(grp);
     // ---- (5) decoder: K, V of the encoder output, Q of the query: thread = projection column
     {
       float wk[kDP], wv[kDP];
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
       }
       Qs[tid] = qd;   // row 0 of Qs
     }
-    __syncthreads();
+    group_sync(grp);
     {  // cross-attention: warp = head, lane = key; softmax across the warp; context: lane = channel of the head
       float a = -INFINITY;
       if (lane < L) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
       __syncwarp();
       Qs[kLdS + warp * kDK + lane] = ctx;   // row 1 of Qs
     }
-    __syncthreads();
+    group_sync(grp);
     if (warp == 0) {  // output projection + residual + LayerNorm + FFN + LayerNorm for the single decoder row: lane = channel
       float o = 0.f;
       if (lane < D) {
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(128) trans_head_kernel(const float* __restrict
       rstd = rsqrtf(warp_sum(dv * dv) / fD + 1e-5f);
       if (lane < D) out[t * D + lane] = dv * rstd * DF[kFfnG + lane] + DF[kFfnB + lane];
     }
-    __syncthreads();   // the tiles are rewritten by the next frame
+    group_sync(grp);   // the tiles are rewritten by the next frame
   }
 }
 
@@ -385,10 +391,10 @@ int sv_trans_forward(sv_trans_handle* h, const float* logits, int64_t ldx, const
   TransParams p;
   p.D = h->cfg.d_model; p.L = h->cfg.len_q; p.FF = h->cfg.d_ff; p.n_videos = n_videos;
   p.scale = 1.0f / sqrtf(static_cast<float>(h->cfg.d_k));
-  const int smem = (kBlobSize + 3 * kLMax * kLdS + 3 * kLMax * kDP + kDP) * static_cast<int>(sizeof(float));
+  const int smem = (kBlobSize + kGroups * kGroupFloats) * static_cast<int>(sizeof(float));
   SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(trans_head_kernel), smem));
-  const int grid = static_cast<int>(std::min<int64_t>(T, std::max(1, device_sm_count())));
-  trans_head_kernel<<<grid, 128, smem, st>>>(logits, ldx, query, h->d_offsets, T, h->d_blob, out, p);
+  const int grid = static_cast<int>(std::min<int64_t>((T + kGroups - 1) / kGroups, std::max(1, device_sm_count())));
+  trans_head_kernel<<<grid, 128 * kGroups, smem, st>>>(logits, ldx, query, h->d_offsets, T, h->d_blob, out, p);
   return launch_status("trans_head_kernel");
 }
 
