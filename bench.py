@@ -40,6 +40,9 @@ FRAMES_PER_VIDEO = 2300
 # (800 = 8.28 waves wasted 8 % of the last wave: measured 123.4 vs 120.8 ms per video on the same box).
 BATCH = 1150
 BATCH_JOB = 1159
+# first batch of the end-to-end ramp-up (then doubling up to the batch size): 96 / 192 / 384 / 768 frames are 0.99 / 1.99 / 3.97 / 7.95
+# waves of stage-3 tiles, so the small batches that let the kernels start early do not waste a partial wave each
+RAMP_START = 96
 FLOPS_PER_FRAME_REF = 16.664e9  # reference graph @224^2 with flow
 FLOPS_PER_FRAME_REF_480 = 166.02e9  # @480x854
 
@@ -435,7 +438,7 @@ def run_video(ctx):
     numa_cpus = lfb.bind_to_gpu_numa_node(ctx.local) if world > 1 else None   # pinned staging memory on the GPU's own NUMA node
     if not a.no_e2e:
         xh, sh, fh = x.cpu().pin_memory(), seg.cpu().pin_memory(), flow.cpu().pin_memory()
-        ext = lfb.LFBExtractor(model, batch_size=B, device=dev)
+        ext = lfb.LFBExtractor(model, batch_size=B, device=dev, ramp_start=RAMP_START if B >= 4 * RAMP_START and (H, W) == (224, 224) else None)
         k = max(1, min(a.steps, 3))
         outs_h = [torch.empty((T, 2048), dtype=torch.float32).pin_memory() for _ in range(k)]
         feats_d = torch.empty((k * T, 2048), dtype=torch.float32, device=dev)
@@ -566,7 +569,7 @@ def run_cholec80(ctx):
     e2e = None
     numa_cpus = lfb.bind_to_gpu_numa_node(ctx.local) if world > 1 else None
     if not a.no_e2e:
-        ext = lfb.LFBExtractor(model, batch_size=B, device=dev)
+        ext = lfb.LFBExtractor(model, batch_size=B, device=dev, ramp_start=RAMP_START if B >= 4 * RAMP_START else None)
         k = 1 if world == 1 else max(1, min(a.steps, 2))
 
         @torch.no_grad()

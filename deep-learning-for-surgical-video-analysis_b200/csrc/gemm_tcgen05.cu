@@ -77,8 +77,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     ptx::prefetch_tensormap(&tmap_a);
     ptx::prefetch_tensormap(&tmap_a2);
     ptx::prefetch_tensormap(&tmap_w);
-    if constexpr ((OUT_F32 || !RESID) && !PAIR) ptx::prefetch_tensormap(&tmap_out);
-    if constexpr (OUT_F32 && RESID && !PAIR) ptx::prefetch_tensormap(&tmap_res);
+    if constexpr (OUT_F32 || !RESID) ptx::prefetch_tensormap(&tmap_out);
+    if constexpr (OUT_F32 && RESID) ptx::prefetch_tensormap(&tmap_res);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -197,7 +197,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // 0: even 32-column chunks, 1: odd chunks
     bool done = false;
-    if constexpr (!OUT_F32 && !RESID && !PAIR) {
+    if constexpr (!OUT_F32 && !RESID) {
       if (p.tma_out) {
       done = true;
       // bf16 result, no residual (fc1, q, kv, sr, adapter, flow and head projections): thread = accumulator row all the way.
@@ -211,7 +211,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t acc_phase = 0;
       uint32_t n_store = 0;   // stores issued by this warp so far (lane 0's bulk groups)
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-        const int m0 = (tile / p.num_n_tiles) * kBlockM;
+        const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = (tile % p.num_n_tiles) * p.block_n;
         const int n_valid = min(p.block_n, p.N - n0);
         const int nchunks = (n_valid + 31) >> 5;
@@ -276,14 +276,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));   // the leader's MMA warp owns both TMEMs
+          else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
       }
     }
-    if constexpr (OUT_F32 && !PAIR) {
+    if constexpr (OUT_F32) {
       if (p.tma_out) {
       done = true;
       // fp32 result, optionally read-modify-write of an fp32 residual (proj / fc2 / shared: x += ...): thread = accumulator row; the
@@ -298,7 +301,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t n_chunk = 0;   // chunks this warp has processed so far: buffer = n_chunk & 1, barrier parity = (n_chunk >> 1) & 1
       const int x = (lane >> 1) & 3;   // 64B swizzle: 16-byte piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-        const int m0 = (tile / p.num_n_tiles) * kBlockM;
+        const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = (tile % p.num_n_tiles) * p.block_n;
         const int n_valid = min(p.block_n, p.N - n0);
         const int nch16 = (n_valid + 15) >> 4;
@@ -389,7 +392,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          if (PAIR) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));
+          else ptx::mbar_arrive(&tmem_empty_bar[acc]);
           if constexpr (RESID) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // both slots free for the next tile's residual loads
         }
         acc ^= 1;
@@ -571,7 +575,7 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.pair = d.pair > 0 ? 1 : 0;
   static const int tma_out_env = getenv("SURGVID_GEMM_TMA_OUT") ? atoi(getenv("SURGVID_GEMM_TMA_OUT")) : 1;   // A/B switch
   // bf16 result without residual, or fp32 result with / without an fp32 residual (the bf16 + residual combination keeps the transposing epilogue)
-  p.tma_out = ((d.out_fp32 || d.residual == nullptr) && !p.pair && tma_out_env) ? 1 : 0;
+  p.tma_out = ((d.out_fp32 || d.residual == nullptr) && tma_out_env) ? 1 : 0;
   if (p.tma_out && d.out_fp32 && ((d.ldc * 4) % 16 != 0 || (d.residual && (d.ldr * 4) % 16 != 0))) p.tma_out = 0;
   p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, (p.tma_out && !d.out_fp32) ? 32 : 16);
   const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
