@@ -364,7 +364,13 @@ class Ctx:
             tpath = os.path.join(ROOT, "profiles", rd, "gemm_traffic.json")
             if os.path.exists(tpath) and (args_hw(self.args) == (224, 224)):
                 tj = json.load(open(tpath))
-                traffic, traffic_src = tj.get("traffic_bytes_per_launch"), tj.get("source")
+                # ncu measured the DRAM bytes of the GEMM launches of one micro-batch of `frames_profiled` frames; per launch of THIS run
+                # (same 197 launches per micro-batch, more frames each) = bytes per frame x frames of this pass / launches of this pass
+                if tj.get("traffic_bytes_per_frame"):
+                    traffic = tj["traffic_bytes_per_frame"] * T / max(1, n_k[0])
+                else:
+                    traffic = tj.get("traffic_bytes_per_launch")
+                traffic_src = tj.get("source")
                 break
         # The dominant kernel is the tcgen05 GEMM.  Its launches have an aggregate arithmetic intensity of ~130 FLOP/B (K = 64..320 for most
         # of them) against a ridge of ~213 FLOP/B, so the BINDING roofline is HBM; the tensor-pipe figures are reported alongside.

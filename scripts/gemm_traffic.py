@@ -30,7 +30,9 @@ for k, c in cls.items():
     print(f"  {k:20s} launches {c['launches']:4d}  time share {c['time']/tot:.3f}  dram rd {c['rd']/1e9:7.2f} GB  wr {c['wr']/1e9:7.2f} GB")
 g = cls.get("gemm_bf16_tcgen05")
 if g and len(sys.argv) > 2:
+    frames = int(sys.argv[4]) if len(sys.argv) > 4 else 800   # frames of the profiled micro-batch
     out = {"kernel": "gemm_bf16_tcgen05_kernel", "traffic_bytes_per_launch": int((g["rd"] + g["wr"]) / g["launches"]), "launches": g["launches"],
+           "frames_profiled": frames, "traffic_bytes_per_frame": (g["rd"] + g["wr"]) / frames,
            "dram_bytes_read": g["rd"], "dram_bytes_write": g["wr"], "source": sys.argv[3] if len(sys.argv) > 3 else path,
            "class_time_shares_under_ncu": {k: round(c["time"] / tot, 4) for k, c in cls.items()}}
     json.dump(out, open(sys.argv[2], "w"), indent=1)
