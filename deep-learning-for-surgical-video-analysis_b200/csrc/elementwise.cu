@@ -265,43 +265,54 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_kernel(const bf16* __re
 // ------------------------------------------------------------------------------------------ Gaussian 5x5 (reflect pad 2)
 __device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
 
-// 32x32 output tile per block (256 threads): the 36x36 reflect-padded input tile goes to shared memory once (coalesced rows), the
-// separable filter runs as a horizontal pass into a second shared tile and a vertical pass out of it — 10 FMAs and ~1.3 global
-// loads per output instead of 25+ cached loads (the direct version was bound by L1 traffic at 1.4 TB/s).  Same FMA order as the
-// direct form (sum over dx first, then over dy), so results are bit-identical to it.
-constexpr int kGT = 32;   // tile edge
+// Register-window version (round 2): a warp owns 28 output columns (32 lanes = 28 + 2 halo columns each side) of a strip of rows and
+// walks down the strip: one 128-byte row load per lane and row, the horizontal 5-tap from warp shuffles, the vertical 5-tap from a
+// rolling window of five horizontally filtered rows in registers.  No shared memory, no block barriers; four row loads are in flight
+// per warp.  Same FMA order as the direct form (sum over dx first, then over dy), so results are bit-identical to the round-1 tiled kernel.
+constexpr int kGW = 28;    // output columns per warp
+constexpr int kGRS = 56;   // output rows per strip (+ 4 halo rows recomputed per strip)
 __global__ void __launch_bounds__(256) gauss5x5_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W) {
-  __shared__ float tin[kGT + 4][kGT + 4 + 1];
-  __shared__ float tmp[kGT + 4][kGT + 1];
-  const int x0 = blockIdx.x * kGT, y0 = blockIdx.y * kGT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (static_cast<int>(blockIdx.x) * 8 + warp) * kGW;
+  if (c0 >= W) return;
+  const int y0 = static_cast<int>(blockIdx.y) * kGRS;
   const int64_t pl = blockIdx.z;
   const float* src = x + pl * H * W;
-  const float k1[5] = {1.f / 16.f, 4.f / 16.f, 6.f / 16.f, 4.f / 16.f, 1.f / 16.f};  // outer(k1,k1) == [1 4 6 4 1]^2 / 256 exactly
-  const int tid = threadIdx.y * 32 + threadIdx.x;
-  for (int i = tid; i < (kGT + 4) * (kGT + 4); i += 256) {
-    const int r = i / (kGT + 4), c = i - r * (kGT + 4);
-    const int gy = reflect_idx(min(y0 + r - 2, H + 1), H), gx = reflect_idx(min(x0 + c - 2, W + 1), W);
-    tin[r][c] = __ldg(src + static_cast<int64_t>(gy) * W + gx);
+  float* dst = out + pl * H * W;
+  const int sc = reflect_idx(min(c0 + lane - 2, W + 1), W);   // source column of this lane (lanes 0,1 / 30,31 are halo columns)
+  const int oc = c0 + lane - 2;
+  const bool wr = lane >= 2 && lane < 2 + kGW && oc < W;
+  const int rows = min(kGRS, H - y0);
+  const float k0 = 1.f / 16.f, k1 = 4.f / 16.f, k2 = 6.f / 16.f;   // outer(k,k) == [1 4 6 4 1]^2 / 256 exactly
+  auto ld = [&](int y) { return __ldg(src + static_cast<int64_t>(reflect_idx(min(y, H + 1), H)) * W + sc); };
+  auto hfilt = [&](float v) {
+    const float xm2 = __shfl_up_sync(0xffffffffu, v, 2), xm1 = __shfl_up_sync(0xffffffffu, v, 1);
+    const float xp1 = __shfl_down_sync(0xffffffffu, v, 1), xp2 = __shfl_down_sync(0xffffffffu, v, 2);
+    float h = fmaf(xm2, k0, 0.f);
+    h = fmaf(xm1, k1, h);
+    h = fmaf(v, k2, h);
+    h = fmaf(xp1, k1, h);
+    return fmaf(xp2, k0, h);
+  };
+  float w0 = hfilt(ld(y0 - 2)), w1 = hfilt(ld(y0 - 1)), w2 = hfilt(ld(y0)), w3 = hfilt(ld(y0 + 1));
+  auto emit = [&](int r, float w4) {
+    float acc = fmaf(w0, k0, 0.f);
+    acc = fmaf(w1, k1, acc);
+    acc = fmaf(w2, k2, acc);
+    acc = fmaf(w3, k1, acc);
+    acc = fmaf(w4, k0, acc);
+    if (wr) dst[static_cast<int64_t>(y0 + r) * W + oc] = acc;
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+  };
+  int r = 0;
+  for (; r + 4 <= rows; r += 4) {   // four independent row loads in flight
+    const float v0 = ld(y0 + r + 2), v1 = ld(y0 + r + 3), v2 = ld(y0 + r + 4), v3 = ld(y0 + r + 5);
+    emit(r, hfilt(v0));
+    emit(r + 1, hfilt(v1));
+    emit(r + 2, hfilt(v2));
+    emit(r + 3, hfilt(v3));
   }
-  __syncthreads();
-  for (int i = tid; i < (kGT + 4) * kGT; i += 256) {
-    const int r = i / kGT, c = i - r * kGT;
-    float v = 0.f;
-#pragma unroll
-    for (int dx = 0; dx < 5; ++dx) v = fmaf(tin[r][c + dx], k1[dx], v);
-    tmp[r][c] = v;
-  }
-  __syncthreads();
-  const int gx = x0 + threadIdx.x;
-#pragma unroll
-  for (int j = 0; j < kGT / 8; ++j) {
-    const int r = threadIdx.y + j * 8;
-    const int gy = y0 + r;
-    float acc = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy) acc = fmaf(tmp[r + dy][threadIdx.x], k1[dy], acc);
-    if (gx < W && gy < H) out[(pl * H + gy) * W + gx] = acc;
-  }
+  for (; r < rows; ++r) emit(r, hfilt(ld(y0 + r + 2)));
 }
 
 // ------------------------------------------------------------------------------------------ bilinear resize (align_corners=False)
@@ -445,9 +456,9 @@ int launch_dwconv3x3_gelu(const bf16* x, const float* w9c, const float* bias, in
 
 int launch_gauss5x5(const float* x, float* out, int planes, int H, int W, cudaStream_t st) {
   SV_CHECK(H >= 3 && W >= 3, "gauss5x5 needs H,W >= 3 (reflect pad 2)");
-  SV_CHECK(planes >= 1 && planes <= 65535 && ceil_div(H, kGT) <= 65535, "gauss5x5 grid limits");
-  dim3 grid(static_cast<unsigned>(ceil_div(W, kGT)), static_cast<unsigned>(ceil_div(H, kGT)), static_cast<unsigned>(planes));
-  gauss5x5_kernel<<<grid, dim3(32, 8), 0, st>>>(x, out, H, W);
+  SV_CHECK(planes >= 1 && planes <= 65535 && ceil_div(H, kGRS) <= 65535, "gauss5x5 grid limits");
+  dim3 grid(static_cast<unsigned>(ceil_div(W, 8 * kGW)), static_cast<unsigned>(ceil_div(H, kGRS)), static_cast<unsigned>(planes));
+  gauss5x5_kernel<<<grid, 256, 0, st>>>(x, out, H, W);
   return launch_status("gauss5x5_kernel");
 }
 
