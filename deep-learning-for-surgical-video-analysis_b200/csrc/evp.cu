@@ -15,6 +15,7 @@
 
 #include <map>
 #include <memory>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -105,13 +106,22 @@ struct Plan {
 struct Arena {
   char* base;
   size_t off = 0;
+  std::vector<std::pair<size_t, size_t>> allocs;   // (offset, bytes) of every buffer handed out, for the bounds check of the plan
   explicit Arena(void* b) : base(static_cast<char*>(b)) {}
   template <typename T>
   T* get(size_t count) {
     off = (off + 255) & ~static_cast<size_t>(255);
     T* p = reinterpret_cast<T*>(base + off);
+    allocs.emplace_back(off, count * sizeof(T));
     off += count * sizeof(T);
     return p;
+  }
+  // does [p, p + bytes) lie inside ONE buffer of the arena?  (a launch that runs past its buffer into a neighbour corrupts silently)
+  bool contains(const void* p, size_t bytes) const {
+    const size_t o = static_cast<size_t>(static_cast<const char*>(p) - base);
+    for (const auto& a : allocs)
+      if (o >= a.first && o + bytes <= a.first + a.second) return true;
+    return false;
   }
 };
 
@@ -446,6 +456,14 @@ struct Builder {
   void gemm(const bf16* A, int64_t lda, const Lin& l, int M, int act, const float* resid, int64_t ldr, void* out, int64_t ldc, int out_fp32,
             const bf16* A2 = nullptr, int64_t lda2 = 0, int K2 = 0) {
     if (dry() || status != SV_OK) return;
+    {  // every GEMM result (and its A operand) must lie inside one workspace buffer
+      const size_t out_bytes = (static_cast<size_t>(M - 1) * ldc + l.N) * (out_fp32 ? 4 : 2);
+      const size_t a_bytes = (static_cast<size_t>(M - 1) * lda + (l.ldw - K2)) * 2;
+      if (!arena.contains(out, out_bytes) || !arena.contains(A, a_bytes)) {
+        status = fail(SV_ERR_STATE, "evp: internal error: a GEMM of the plan addresses memory outside its workspace buffer");
+        return;
+      }
+    }
     GemmDesc d;
     d.A = A; d.lda = lda; d.W = W(l); d.ldw = l.ldw; d.M = M; d.N = l.N; d.bias = Bf(l); d.act = act;
     d.A2 = A2; d.lda2 = lda2; d.K2 = K2;
