@@ -400,6 +400,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // current one is being used.  Tile j of the CTA belongs to softmax group j & 1 (ping-pong, S and O double-buffered in TMEM).
 struct AttnTcSingleParams {
   int Nq, Nkv, heads, qtiles, tiles_total;
+  int order;   // 1: head fastest, items dealt round-robin (several heads); 0: contiguous (frame, head, tile) ranges
   float scale_log2;
 };
 
@@ -413,8 +414,25 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = p.tiles_total / static_cast<int>(gridDim.x), extra = p.tiles_total % static_cast<int>(gridDim.x);
-  const int t_begin = static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), extra);
   const int ntiles = per + (static_cast<int>(blockIdx.x) < extra ? 1 : 0);
+  // Work-item order.  One head: a contiguous range of (frame, query tile) items per CTA (K/V loaded once per frame).  Several heads: the
+  // head index runs FASTEST and items are dealt round-robin, so the CTAs running at the same time read / write all heads of the same
+  // token rows (whole C-wide rows per DRAM page instead of one 128-byte head slice of every row: with the head outermost the achieved
+  // bandwidth fell with the head count, 4.5 / 3.4 / 2.3 / 1.6 TB/s at 1 / 2 / 5 / 8 heads); K/V (16 KB, L2-resident) are then loaded per item.
+  const bool rr = p.order != 0 && p.heads > 1;
+  const int t_first = rr ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * per + min(static_cast<int>(blockIdx.x), extra);
+  const int t_stride = rr ? static_cast<int>(gridDim.x) : 1;
+  auto item = [&](int j, int& bh, int& qt) {   // j-th item of this CTA -> (frame * heads + head, query tile)
+    const int t = t_first + j * t_stride;
+    if (rr) {
+      const int head = t % p.heads, r = t / p.heads;
+      qt = r % p.qtiles;
+      bh = (r / p.qtiles) * p.heads + head;
+    } else {
+      bh = t / p.qtiles;
+      qt = t - bh * p.qtiles;
+    }
+  };
   uint8_t* smem = attn_tc_smem + ((1024u - (ptx::smem_u32(attn_tc_smem) & 1023u)) & 1023u);
   uint8_t* Qs = smem;                       // [2][16 KB]
   uint8_t* Ks = Qs + 2 * kQBytes;           // [2][8 KB]  K of the current / the next (frame, head)
@@ -459,7 +477,9 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       if (lane == 0) {
         int prev_bh = -1, n_kv = 0;
         for (int j = 0; j < ntiles; ++j) {
-          const int t = t_begin + j, bh = t / p.qtiles, qt = t - bh * p.qtiles, b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
+          int bh, qt;
+          item(j, bh, qt);
+          const int b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
           if (bh != prev_bh) {
             const int kb = n_kv & 1;
             if (n_kv >= 2) ptx::mbar_wait(&kv_empty[kb], static_cast<uint32_t>(((n_kv - 2) >> 1) & 1));   // every MMA on the pair two back has retired
@@ -479,7 +499,9 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       // ---------------------------------------------------------------- TMA stores of the output tiles (warp 11 idles)
       if (lane == 0) {
         for (int j = 0; j < ntiles; ++j) {
-          const int t = t_begin + j, bh = t / p.qtiles, qt = t - bh * p.qtiles, b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
+          int bh, qt;
+          item(j, bh, qt);
+          const int b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
           const int sb = j & 1;
           ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((j >> 1) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
           tma_store_3d(&tmap_o, Ps + sb * kQBytes, c0, qt * kQRows, b);
@@ -498,7 +520,8 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         int bh_pv = -1, kb_pv = 0;           // ... and of the tile whose PV is being issued (one tile behind)
         for (int j = 0; j <= ntiles; ++j) {
           if (j < ntiles) {
-            const int bh = (t_begin + j) / p.qtiles;
+            int bh, qt_unused;
+            item(j, bh, qt_unused);
             if (bh != bh_s) {
               kb_s = n_kv & 1;
               ptx::mbar_wait(&kv_full[kb_s], static_cast<uint32_t>((n_kv >> 1) & 1));
@@ -518,7 +541,8 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           }
           if (j >= 1) {
             const int jj = j - 1, g = jj & 1;
-            const int bh = (t_begin + jj) / p.qtiles;
+            int bh, qt_unused;
+            item(jj, bh, qt_unused);
             if (bh != bh_pv) { kb_pv = (bh_pv < 0) ? 0 : (kb_pv ^ 1); bh_pv = bh; }   // pairs alternate buffers in issue order
             // P_jj is in shared memory; the same arrivals order the group's reads of S_jj and of O_{jj-2} before this point
             ptx::mbar_wait(&p_full[g], static_cast<uint32_t>((jj >> 1) & 1));
@@ -531,7 +555,9 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
                             ks ? 1u : 0u);
             ptx::umma_commit(&o_full[g]);
             // last tile of its (frame, head): once everything issued so far has retired, the K/V buffer may be refilled
-            if (j == ntiles || (t_begin + j) / p.qtiles != bh) ptx::umma_commit(&kv_empty[kb_pv]);
+            int bh_next = -1;
+            if (j < ntiles) item(j, bh_next, qt_unused);
+            if (j == ntiles || bh_next != bh) ptx::umma_commit(&kv_empty[kb_pv]);
           }
         }
       }
@@ -547,7 +573,8 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     uint8_t* Pg = Ps + grp * kQBytes;
     for (int j = grp; j < ntiles; j += 2) {
       const uint32_t par = static_cast<uint32_t>((j >> 1) & 1);
-      const int qt = (t_begin + j) % p.qtiles;
+      int bh_unused, qt;
+      item(j, bh_unused, qt);
       const bool active = qt * kQRows + quarter * 32 < p.Nq;   // warp-uniform: rows past the frame's last query do no math
       ptx::mbar_wait(&s_full[grp], par);
       ptx::tc_fence_after();
@@ -683,6 +710,8 @@ int attention_tc_launch(const AttnTcPlan& plan, cudaStream_t st) {
   } else {
     AttnTcSingleParams sp;
     sp.Nq = plan.Nq; sp.Nkv = plan.Nkv; sp.heads = plan.heads; sp.qtiles = plan.qtiles; sp.scale_log2 = plan.scale_log2;
+    static const int order_env = [] { const char* e = getenv("SURGVID_ATTN_ORDER"); return e ? atoi(e) : 0; }();
+    sp.order = order_env;
     const long long total = static_cast<long long>(plan.B) * plan.heads * plan.qtiles;
     if (total >= (1LL << 31)) return fail(SV_ERR_INVALID, "attention_tc: more than 2^31 query tiles");
     sp.tiles_total = static_cast<int>(total);

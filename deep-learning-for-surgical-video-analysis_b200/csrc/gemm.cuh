@@ -35,6 +35,9 @@ struct GemmParams {
   int pair;         // 1: 2-CTA clusters; num_tiles counts 256-row pair tiles
   int prefetch;     // k-blocks of the A operand requested into L2 ahead of the shared-memory ring (0 = off)
   int kb_split;     // k-blocks served by the first A segment (all of them without a second segment)
+  int epi_bufs;     // TMA epilogues: 2 KB staging buffers per epilogue warp (2..4) = result stores / residual loads in flight per warp
+  int epi_lag;      // fp32 + residual: result stores allowed to be pending when a buffer is handed back to the residual loads (1..epi_bufs-1)
+  int staging_bytes;  // shared memory between the operand ring and the bias slices
   int tma_out;      // 1: bf16 result without residual is written with 2-D TMA stores from a swizzled staging tile
   int act;
   int out_fp32;

@@ -38,10 +38,11 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kTmemCols = 512;                    // 2 accumulator buffers x 256 columns
 constexpr int kAccStride = 256;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
-constexpr int kSmemBudget = 184320;               // operand ring budget (bytes), + 1 KB alignment slack
-constexpr int kStagingBytes = kEpiWarps * 32 * kStageLd * 4;  // per epilogue warp: 32 rows x 36 floats
+constexpr int kStagingBytes = kEpiWarps * 32 * kStageLd * 4;  // transposing epilogue, per warp: 32 rows x 36 floats
 constexpr int kBiasBytes = kEpiWarps * 256 * 4;   // per epilogue warp: this tile's 256 bias values
-constexpr int kEpiSmemBytes = kStagingBytes + kBiasBytes;
+constexpr int kMaxEpiBufs = 4;                    // TMA epilogues: 2 KB staging buffers per warp
+constexpr int kEpiBufBytes = 2048;
+constexpr int kSmemTotal = 230400;                // dynamic shared memory per CTA: 1 KB alignment slack + operand ring + staging + bias
 
 // PAIR = true: the kernel runs as 2-CTA clusters (tcgen05 cta_group::2).  Each CTA stages its own 128 rows of A and HALF of
 // the B tile (block_n/2 rows); the leader CTA (cluster rank 0) issues one M=256 MMA per k-step that reads both CTAs' shared
@@ -58,7 +59,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(8) uint64_t res_full[kEpiWarps][2];   // fp32 TMA epilogue: residual chunk landed in the warp's staging buffer
+  __shared__ __align__(8) uint64_t res_full[kEpiWarps][kMaxEpiBufs];   // fp32 TMA epilogue: residual chunk landed in the warp's staging buffer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -71,7 +72,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   // (offset arithmetic on the __shared__ array keeps the address space visible to the compiler: LDS/STS, not generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   float* staging = reinterpret_cast<float*>(smem + S * stage_bytes);  // epilogue transpose tiles live behind the operand ring
-  float* bias_smem = staging + kEpiWarps * 32 * kStageLd;
+  float* bias_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(staging) + p.staging_bytes);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_a);
@@ -86,10 +87,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
       }
-      for (int w = 0; w < kEpiWarps; ++w) {
-        ptx::mbar_init(&res_full[w][0], 1);
-        ptx::mbar_init(&res_full[w][1], 1);
-      }
+      for (int w = 0; w < kEpiWarps; ++w)
+        for (int b = 0; b < kMaxEpiBufs; ++b) ptx::mbar_init(&res_full[w][b], 1);
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full_bar[a], 1);
         ptx::mbar_init(&tmem_empty_bar[a], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
@@ -117,7 +116,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop in lock step and polls the barriers; one elected lane issues the TMA instructions (see ptx::elect_one).
+    {
       int stage = 0;
       uint32_t phase = 0;
       // L2 prefetch cursor: runs p.prefetch k-blocks ahead of the load cursor over this CTA's (tile, k-block) sequence
@@ -125,7 +125,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       auto prefetch_next = [&]() {
         if (pf_tile >= p.num_tiles) return;
         const int pm0 = (pf_tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
-        ptx::tma_prefetch_l2_2d(&tmap_a, pf_kb * kBlockK, pm0);
+        if (ptx::elect_one()) ptx::tma_prefetch_l2_2d(&tmap_a, pf_kb * kBlockK, pm0);
         if (++pf_kb == num_kb) { pf_kb = 0; pf_tile += tile_step; }
       };
       for (int i = 0; i < p.prefetch; ++i) prefetch_next();
@@ -140,23 +140,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const bool seg2 = kb >= p.kb_split;   // second A segment (e.g. the adapter tensor next to the MixFFN hidden)
           const CUtensorMap* ma = seg2 ? &tmap_a2 : &tmap_a;
           const int ka = (seg2 ? kb - p.kb_split : kb) * kBlockK;
-          if (PAIR) {
-            // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
-            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
-            ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], ka, m0);
-            ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
-          } else {
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
-            ptx::tma_load_2d(sa, ma, &full_bar[stage], ka, m0);
-            ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+          if (ptx::elect_one()) {
+            if (PAIR) {
+              // the leader's barrier collects the bytes of both CTAs; only the leader posts the expectation
+              if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(2 * stage_bytes));
+              ptx::tma_load_2d_pair(sa, ma, &full_bar[stage], ka, m0);
+              ptx::tma_load_2d_pair(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+            } else {
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(stage_bytes));
+              ptx::tma_load_2d(sa, ma, &full_bar[stage], ka, m0);
+              ptx::tma_load_2d(sb, &tmap_w, &full_bar[stage], kb * kBlockK, n0);
+            }
           }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // Converged warp, one elected lane issues: four tcgen05.mma per 64-deep k-block, fully unrolled, then the commits.  (Measured,
+    // scripts/ubench/umma_rate.cu: a single divergent thread with a run-time k-step loop needs ~195 cycles per N = 256 MMA against
+    // the pipe's 128; this form reaches 128.)
+    if (cta_rank == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16_f32(PAIR ? 2 * kBlockM : kBlockM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
@@ -173,19 +179,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
           const uint64_t db = ptx::make_sw128_kmajor_desc(sa + kATileBytes);
           const int k_left = p.K - kb * kBlockK;
-          const int ksteps = k_left >= kBlockK ? kBlockK / 16 : (k_left + 15) / 16;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) start-address field
-            if (PAIR) ptx::umma_f16_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
-            else ptx::umma_f16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
-          if (PAIR) {
-            ptx::umma_commit_pair(&empty_bar[stage], 0x3);                          // both CTAs' smem slots
-            if (kb == num_kb - 1) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);  // both CTAs' epilogues
+          const bool last = kb == num_kb - 1;
+          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr>>4) start-address field
+          if (k_left >= kBlockK) {
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < kBlockK / 16; ++kk) {
+                const uint32_t accum = (kk != 0 || kb != 0) ? 1u : 0u;
+                if (PAIR) ptx::umma_f16_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, accum);
+                else ptx::umma_f16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, accum);
+              }
+              if (PAIR) {
+                ptx::umma_commit_pair(&empty_bar[stage], 0x3);                 // both CTAs' smem slots
+                if (last) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);     // both CTAs' epilogues
+              } else {
+                ptx::umma_commit(&empty_bar[stage]);                           // smem slot reusable once these MMAs retire
+                if (last) ptx::umma_commit(&tmem_full_bar[acc]);               // accumulator ready for the epilogue
+              }
+            }
           } else {
-            ptx::umma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
-            if (kb == num_kb - 1) ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+            const int ksteps = (k_left + 15) / 16;   // ragged K tail (TMA zero-fills the rest of the row)
+            if (ptx::elect_one()) {
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint32_t accum = (kk != 0 || kb != 0) ? 1u : 0u;
+                if (PAIR) ptx::umma_f16_pair(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, accum);
+                else ptx::umma_f16(d_tmem, da + static_cast<uint64_t>(kk * 2), db + static_cast<uint64_t>(kk * 2), idesc, accum);
+              }
+              if (PAIR) {
+                ptx::umma_commit_pair(&empty_bar[stage], 0x3);
+                if (last) ptx::umma_commit_pair(&tmem_full_bar[acc], 0x3);
+              } else {
+                ptx::umma_commit(&empty_bar[stage]);
+                if (last) ptx::umma_commit(&tmem_full_bar[acc]);
+              }
+            }
           }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1u; }
         }
         acc ^= 1;
@@ -205,7 +234,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // 2-D TMA store (box 32 columns x 32 rows; ragged M / N edges are clipped by the tensor map) — no transposition through
       // shared memory and no per-thread global stores.  (ncu, round 2: the transposing epilogue ran the L1TEX LSU data pipe at
       // 72-75 % on these GEMMs — 81 shared/global wavefronts per 32x32 block against 24 here.)
-      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 4096;   // two 2 KB buffers, 1 KB aligned
+      const uint32_t nb = static_cast<uint32_t>(p.epi_bufs);
+      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * p.epi_bufs * kEpiBufBytes;   // nb 2 KB buffers, 1 KB aligned
       float* bias_s = bias_smem + (warp - 2) * 256;
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -229,9 +259,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         uint32_t r_a[32], r_b[32];
         if (half < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(half * 32), r_a);
         auto emit = [&](const uint32_t (&r)[32], int c) {
-          uint8_t* sb = sbase + (n_store & 1u) * 2048;
-          if (n_store >= 2u) {   // the store issued from this buffer two chunks ago has finished reading it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          uint8_t* sb = sbase + (n_store % nb) * kEpiBufBytes;
+          if (n_store >= nb) {   // the store issued from this buffer nb chunks ago has finished reading it
+            if (ptx::elect_one()) ptx::bulk_wait_group_read(static_cast<int>(nb) - 1);
             __syncwarp();
           }
           uint32_t w[16];
@@ -257,7 +287,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             *reinterpret_cast<uint4*>(sb + lane * 64 + ((j ^ x) << 4)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)),
                          "r"(ptx::smem_u32(sb)), "r"(n0 + c * 32), "r"(m0 + quarter * 32)
                          : "memory");
@@ -283,48 +313,69 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
+      if (ptx::elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
       }
     }
     if constexpr (OUT_F32) {
       if (p.tma_out) {
       done = true;
       // fp32 result, optionally read-modify-write of an fp32 residual (proj / fc2 / shared: x += ...): thread = accumulator row; the
-      // residual arrives by 2-D TMA loads (box 16 columns x 32 rows, 64-byte swizzle) into a 2-deep per-warp ring, issued while the
-      // tile's MMAs are still running; the row is updated in place in shared memory and leaves through a TMA store of the same box.
-      // No transposition, no per-thread global loads/stores, no long-scoreboard stalls on the residual stream.
-      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * 4096;   // two 2 KB buffers, 1 KB aligned
+      // residual arrives by 2-D TMA loads (box 16 columns x 32 rows, 64-byte swizzle) into a per-warp ring of nb 2 KB buffers, the
+      // row is updated in place in shared memory and leaves through a TMA store of the same box.  The ring runs CONTINUOUSLY over
+      // the warp's chunks of all its tiles: after the store of chunk i the warp waits only until the store of chunk i - lag has
+      // finished reading its buffer and hands that buffer to the load of chunk i - lag + nb, so nb - lag residual loads and lag
+      // result stores are in flight per warp, across tile boundaries (the residual of the next tile streams in while this tile's
+      // MMAs and epilogue are still running).  No transposition, no per-thread global loads/stores.
+      // (Round 2 measurement that led here, profiles/r02/gemm_operand_stream_experiment.log: with NO operand loads at all the
+      // K = 1360 residual GEMM took 177 of 202 us — the kernel was bound by this epilogue: a 2-deep ring and a blocking wait for
+      // every store kept only ~3 KB per warp in flight.)
+      const uint32_t nb = static_cast<uint32_t>(p.epi_bufs), lag = static_cast<uint32_t>(p.epi_lag);
+      uint8_t* sbase = reinterpret_cast<uint8_t*>(staging) + (warp - 2) * p.epi_bufs * kEpiBufBytes;   // nb 2 KB buffers, 1 KB aligned
       float* bias_s = bias_smem + (warp - 2) * 256;
       uint64_t* rbar = res_full[warp - 2];
       int acc = 0;
       uint32_t acc_phase = 0;
-      uint32_t n_chunk = 0;   // chunks this warp has processed so far: buffer = n_chunk & 1, barrier parity = (n_chunk >> 1) & 1
+      uint32_t n_chunk = 0;    // chunks this warp has processed so far: buffer = n_chunk % nb, barrier parity = (n_chunk / nb) & 1
+      uint32_t n_loaded = 0;   // residual loads issued so far (same numbering)
       const int x = (lane >> 1) & 3;   // 64B swizzle: 16-byte piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
+      const int m_step = PAIR ? 2 * kBlockM : kBlockM;
+      auto chunks_of = [&](int n0) {   // this warp takes the 16-column chunks half, half + 2, ... of a tile
+        const int nch16 = (min(p.block_n, p.N - n0) + 15) >> 4;
+        return (nch16 - half + 1) >> 1;
+      };
+      int ld_tile = first_tile, ld_k = 0;   // residual load cursor
+      auto issue_load = [&]() {
+        while (ld_tile < p.num_tiles) {
+          const int ln0 = (ld_tile % p.num_n_tiles) * p.block_n;
+          if (ld_k < chunks_of(ln0)) {
+            if (ptx::elect_one()) {
+              const uint32_t slot = n_loaded % nb;
+              const int lm0 = (ld_tile / p.num_n_tiles) * m_step + static_cast<int>(cta_rank) * kBlockM;
+              ptx::mbar_arrive_expect_tx(&rbar[slot], static_cast<uint32_t>(kEpiBufBytes));
+              ptx::tma_load_2d(sbase + slot * kEpiBufBytes, &tmap_res, &rbar[slot], ln0 + (half + 2 * ld_k) * 16, lm0 + quarter * 32);
+            }
+            ++n_loaded;
+            ++ld_k;
+            return;
+          }
+          ld_k = 0;
+          ld_tile += tile_step;
+        }
+      };
+      if constexpr (RESID) {
+        for (uint32_t i = 0; i < nb - lag; ++i) issue_load();
+      }
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
-        const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
+        const int m0 = (tile / p.num_n_tiles) * m_step + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = (tile % p.num_n_tiles) * p.block_n;
         const int n_valid = min(p.block_n, p.N - n0);
-        const int nch16 = (n_valid + 15) >> 4;
-        const int my_chunks = (nch16 - half + 1) >> 1;          // this warp takes 16-column chunks half, half + 2, ...
-        auto load_res = [&](int k) {                             // k-th chunk of this warp in this tile -> ring slot (n_chunk + k) & 1
-          if (lane == 0) {
-            const uint32_t slot = (n_chunk + static_cast<uint32_t>(k)) & 1u;
-            ptx::mbar_arrive_expect_tx(&rbar[slot], 2048u);
-            ptx::tma_load_2d(sbase + slot * 2048, &tmap_res, &rbar[slot], n0 + (half + 2 * k) * 16, m0 + quarter * 32);
-          }
-        };
+        const int my_chunks = chunks_of(n0);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int c = i * 128 + lane * 4;
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias != nullptr && c < n_valid) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c));
           *reinterpret_cast<float4*>(bias_s + c) = b;
-        }
-        if constexpr (RESID) {
-          // both ring slots are free here: every store of the previous tile was waited for (wait_group.read) before its slot was
-          // refilled or, for the last two, right below at the end of the tile
-          if (my_chunks > 0) load_res(0);
-          if (my_chunks > 1) load_res(1);
         }
         __syncwarp();
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -334,14 +385,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (my_chunks > 0) ptx::tmem_ld_x16(t_row + static_cast<uint32_t>(half * 16), r_a);
         auto emit = [&](const uint32_t (&r)[16], int k) {
           const int c16 = half + 2 * k;
-          const uint32_t slot = n_chunk & 1u;
-          uint8_t* sb = sbase + slot * 2048;
+          const uint32_t slot = n_chunk % nb;
+          uint8_t* sb = sbase + slot * kEpiBufBytes;
           float* rowp = reinterpret_cast<float*>(sb + lane * 64);
           if constexpr (RESID) {
-            ptx::mbar_wait(&rbar[slot], (n_chunk >> 1) & 1u);
+            ptx::mbar_wait(&rbar[slot], (n_chunk / nb) & 1u);
           } else {
-            if (n_chunk >= 2u) {   // the store issued from this slot two chunks ago has finished reading it
-              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (n_chunk >= nb) {   // the store issued from this buffer nb chunks ago has finished reading it
+              if (ptx::elect_one()) ptx::bulk_wait_group_read(static_cast<int>(nb) - 1);
               __syncwarp();
             }
           }
@@ -364,21 +415,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmap_out)),
                          "r"(ptx::smem_u32(sb)), "r"(n0 + c16 * 16), "r"(m0 + quarter * 32)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if constexpr (RESID) {
-              if (k + 2 < my_chunks) {   // refill this slot with the residual of the chunk after next once the store has read it
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                const uint32_t s2 = slot;
-                ptx::mbar_arrive_expect_tx(&rbar[s2], 2048u);
-                ptx::tma_load_2d(sb, &tmap_res, &rbar[s2], n0 + (c16 + 4) * 16, m0 + quarter * 32);
-              }
-            }
+            // the buffer of chunk n_chunk - lag is free once its store has read it: at most lag younger stores may still be pending
+            if constexpr (RESID) ptx::bulk_wait_group_read(static_cast<int>(lag));
           }
           ++n_chunk;
+          if constexpr (RESID) issue_load();   // chunk n_chunk - 1 - lag + nb, into the buffer just freed
         };
         for (int k = 0; k < my_chunks; k += 2) {
           ptx::tmem_ld_wait();
@@ -394,12 +440,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
           if (PAIR) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));
           else ptx::mbar_arrive(&tmem_empty_bar[acc]);
-          if constexpr (RESID) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // both slots free for the next tile's residual loads
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
+      if (ptx::elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory stays valid until the last store has read it
       }
     }
     if (!done) {
@@ -572,22 +617,40 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   SV_CHECK(sms > 0, "no CUDA device");
   GemmParams& p = plan->p;
   p.M = d.M; p.N = d.N; p.K = d.K;
-  p.pair = d.pair > 0 ? 1 : 0;
   static const int tma_out_env = getenv("SURGVID_GEMM_TMA_OUT") ? atoi(getenv("SURGVID_GEMM_TMA_OUT")) : 1;   // A/B switch
   // bf16 result without residual, or fp32 result with / without an fp32 residual (the bf16 + residual combination keeps the transposing epilogue)
   p.tma_out = ((d.out_fp32 || d.residual == nullptr) && tma_out_env) ? 1 : 0;
   if (p.tma_out && d.out_fp32 && ((d.ldc * 4) % 16 != 0 || (d.residual && (d.ldr * 4) % 16 != 0))) p.tma_out = 0;
   p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, (p.tma_out && !d.out_fp32) ? 32 : 16);
-  const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
-  // CTA-pair mode pays off when operand staging (L2 -> smem) dominates: deep K and enough 256-row tiles to fill the machine
-  // Measured on B200 (profiles/r01/gemm_pair_vs_single.log): at this path's shapes the pair mode is 5-20 % SLOWER than single-CTA
-  // tiles, so 'auto' resolves to off; the mode stays available (and tested) behind GemmDesc::pair / SURGVID_GEMM_PAIR.
-  p.pair = d.pair > 0 ? 1 : 0;
+  // CTA-pair mode (cta_group::2): each CTA stages half of the B tile, so the ring holds more k-blocks per byte of shared memory.
+  // Measured on B200 (profiles/r02/gemm_elect.log, after the MMA issue moved to a converged warp + elect.sync): it wins where the
+  // k-loop dominates — K = 1280..8192: 184 -> 172 us (156 800 x 320 x 1360 + residual), 1015 -> 902 us (39 200 x 2048 x 8192 =
+  // 1.46 PFLOP/s), 247 -> 224 us (K = 2176) — and loses 15-35 % on the K <= 320 GEMMs, whose time is the epilogue's (two CTAs'
+  // epilogues gate every accumulator hand-back).  'auto' (-1) therefore enables it for K >= 1024 when there are enough 256-row tiles
+  // to fill the machine; GemmDesc::pair / SURGVID_GEMM_PAIR force it on (1) or off (0).
+  {
+    static const int pair_env = getenv("SURGVID_GEMM_PAIR") ? atoi(getenv("SURGVID_GEMM_PAIR")) : -1;
+    const int want = d.pair >= 0 ? d.pair : pair_env;
+    const long long pair_tiles = static_cast<long long>(ceil_div(d.M, 2 * kBlockM)) * ceil_div(d.N, p.block_n);
+    p.pair = want >= 0 ? (want > 0 ? 1 : 0) : ((d.K >= 1024 && pair_tiles >= sms / 2) ? 1 : 0);
+  }
   if (p.pair && (p.block_n % 32 != 0)) p.block_n = round_up(p.block_n, 32);  // each CTA stages block_n/2 rows of B (multiple of 16)
   if (p.block_n > 256) { p.block_n = 256; }
   const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
   const int stage_bytes_eff = kATileBytes + b_rows * kBlockK * 2;
-  p.num_stages = std::min(kMaxStages, kSmemBudget / stage_bytes_eff);
+  // shared-memory split: [1 KB alignment slack | operand ring | epilogue staging | bias slices] = kSmemTotal.  The TMA epilogues keep
+  // epi_bufs 2 KB buffers per warp in flight (stores, and residual loads for the read-modify-write form); measured (round 2) they,
+  // not the operand ring, bound the K <= 1360 GEMMs, so they get 4 buffers and the ring what is left (>= 3 stages at every block_n)
+  {
+    static const int bufs_env = getenv("SURGVID_GEMM_EPI_BUFS") ? atoi(getenv("SURGVID_GEMM_EPI_BUFS")) : kMaxEpiBufs;
+    static const int lag_env = getenv("SURGVID_GEMM_EPI_LAG") ? atoi(getenv("SURGVID_GEMM_EPI_LAG")) : 1;
+    p.epi_bufs = std::min(kMaxEpiBufs, std::max(2, bufs_env));
+    p.epi_lag = std::min(p.epi_bufs - 1, std::max(1, lag_env));
+    p.staging_bytes = p.tma_out ? kEpiWarps * p.epi_bufs * kEpiBufBytes : kStagingBytes;
+  }
+  const int ring_budget = kSmemTotal - 1024 - kBiasBytes - p.staging_bytes;
+  p.num_stages = std::min(kMaxStages, ring_budget / stage_bytes_eff);
+  SV_CHECK(p.num_stages >= 2, "GEMM shared-memory plan");
   p.num_n_tiles = ceil_div(d.N, p.block_n);
   p.num_tiles = ceil_div(d.M, p.pair ? 2 * kBlockM : kBlockM) * p.num_n_tiles;
   {
@@ -597,7 +660,7 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.act = d.act; p.out_fp32 = d.out_fp32;
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.out = d.out; p.ldc = d.ldc;
   plan->grid = p.pair ? 2 * std::min(p.num_tiles, sms / 2) : std::min(p.num_tiles, sms);
-  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes_eff + kEpiSmemBytes + 1024;
+  plan->smem_bytes = static_cast<size_t>(p.num_stages) * stage_bytes_eff + p.staging_bytes + kBiasBytes + 1024;
   plan->flops = 2.0 * d.M * static_cast<double>(d.N) * d.K;
   p.kb_split = ceil_div(d.K - d.K2, kBlockK);
   SV_TRY(encode_operand_map(&plan->tmap_a, d.A, d.M, d.K - d.K2, d.lda, kBlockM));
@@ -657,7 +720,7 @@ GemmKernelFn kernel_for(const GemmParams& p) {
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   GemmKernelFn fn = kernel_for(plan.p);
-  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), kSmemBudget + kEpiSmemBytes + 1024));
+  SV_TRY(ensure_dynamic_smem(reinterpret_cast<const void*>(fn), kSmemTotal));
   if (plan.p.pair) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan.grid);

@@ -51,6 +51,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One leader lane of a CONVERGED warp (the same lane every time for the full mask).  tcgen05.mma / tcgen05.commit / TMA instructions take
+// their operands from uniform registers: issued under `if (lane == 0)` the compiler wraps every one of them in a serialising
+// BRA.U.ANY loop with R2UR moves, issued under elect.sync inside warp-uniform control flow they are emitted back to back
+// (scripts/ubench/umma_rate.cu: 570 -> 512 cycles per 4-MMA group at N = 256, 571 -> 457 at N = 160).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -64,6 +80,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// cp.async.bulk.wait_group.read takes an immediate: at most n (0..3) of this thread's bulk store groups may still be reading shared memory
+__device__ __forceinline__ void bulk_wait_group_read(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+  }
+}
 // Ask the TMA unit to pull a tile into L2 only (no shared-memory destination, no barrier): used to run the HBM stream well
 // ahead of the shared-memory ring, whose depth alone cannot cover DRAM latency for short-K GEMMs.
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {

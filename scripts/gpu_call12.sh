@@ -1,12 +1,24 @@
 #!/bin/bash
-O=gpurun_out/r02; mkdir -p $O
-timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q -k "stem or gauss" > $O/pytest_j.log 2>&1; echo "stem/gauss tests rc=$?"; tail -2 $O/pytest_j.log | cut -c1-200
-timeout 900 python -m pytest tests/test_evp_gpu.py -m gpu -x -q -s -k "golden or ragged or 480 or variants" > $O/pytest_j_evp.log 2>&1; echo "evp rc=$?"; tail -1 $O/pytest_j_evp.log; grep "parity\] ref_init feats vs\|parity\] stress feats vs" $O/pytest_j_evp.log
-REPS=20 python scripts/op_bench.py stem 2>&1 | tee $O/stem_bench2.log
-REPS=20 python scripts/op_bench.py im2col 2>&1 | grep gauss | tee -a $O/stem_bench2.log
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > $O/bench_j.json 2>/dev/null; python - <<'PY'
+# A/B of the DRAM-locality work orders (DWConv channel block fastest, attention head fastest), then the affected tests and a short bench.
+mkdir -p gpurun_out/r02
+{
+for o in 0 1; do
+  echo "== DW_ORDER=$o ATTN_ORDER=$o B=200"; SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py dwconv
+  SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py attn
+  echo "== DW_ORDER=$o ATTN_ORDER=$o B=1159"; SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py dwconv
+  SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py attn
+done
+} > gpurun_out/r02/order_ab.txt 2>&1
+timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "dwconv or attention" > gpurun_out/r02/order_tests.txt 2>&1; echo "tests rc=$?"
+for o in "0 0" "1 0" "0 1" "1 1"; do set -- $o
+  SURGVID_DW_ORDER=$1 SURGVID_ATTN_ORDER=$2 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/r02/order_bench_$1$2.json 2> gpurun_out/r02/order_bench_$1$2.err; echo "bench $1 $2 rc=$?"
+done
+tail -3 gpurun_out/r02/order_tests.txt
+cat gpurun_out/r02/order_ab.txt
+python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r02/bench_j.json').read().strip().splitlines()[-1])
-k=d['kernel_classes']
-print('value',round(d['value']),'ms',round(d['ms_per_step'],2),{n:round(v['ms'],2) for n,v in k.items() if v['ms']>1},d['clocks']['sm_mhz'])
+for k in ("00","10","01","11"):
+    try:
+        d=json.loads(open(f"gpurun_out/r02/order_bench_{k}.json").read().strip().splitlines()[-1]); print(k, d["value"], d["ms_per_step"], d["clocks"]["sm_mhz"])
+    except Exception as e: print(k, "ERR", e)
 PY

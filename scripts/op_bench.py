@@ -18,7 +18,7 @@ def timeit(name, fn, nbytes):
     us = e0.elapsed_time(e1) / reps * 1e3
     print(f"{name}: {us:8.1f} us  {nbytes/us/1e3:7.1f} GB/s", flush=True)
 
-B = 200
+B = int(os.environ.get("B", "200"))
 if which in ("all", "dwconv"):
     for (H, W, C) in [(14, 14, 1280), (56, 56, 256), (28, 28, 512), (7, 7, 2048)]:
         x = torch.randn(B, H, W, C, device=dev).bfloat16(); w = torch.randn(9, C, device=dev); b = torch.randn(C, device=dev)
