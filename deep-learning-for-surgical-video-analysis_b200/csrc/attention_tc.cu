@@ -173,34 +173,41 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");   // one instruction for the whole control warpgroup (warps 8-11)
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA loads
-    if (lane == 0) {
+    // (all three control warps: the whole warp runs the loop and polls the barriers, ONE ELECTED lane issues the TMA / tcgen05
+    // instructions — issued under `if (lane == 0)` every one of them is wrapped in a serialising BRA.U.ANY loop, see ptx::elect_one)
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(&kv_full, static_cast<uint32_t>(2 * kt * kKBytes));
       for (int t = 0; t < kt; ++t) {
         tma_load_3d(Ks + t * kKBytes, &tmap_k, &kv_full, c0, t * kKeys, b);
         tma_load_3d(Vs + t * kKBytes, &tmap_v, &kv_full, c0, t * kKeys, b);
       }
-      for (int j = 0; j < ntiles; ++j) {
-        const int qb = j & 1;
-        if (j >= 2) ptx::mbar_wait(&q_empty[qb], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // the S MMAs of tile j-2 have read this buffer
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      const int qb = j & 1;
+      if (j >= 2) ptx::mbar_wait(&q_empty[qb], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // the S MMAs of tile j-2 have read this buffer
+      if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&q_full[qb], kQBytes);
         tma_load_3d(Qs + qb * kQBytes, &tmap_q, &q_full[qb], c0, (tile0 + j) * kQRows, b);
       }
+      __syncwarp();
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------------ TMA stores of the output tiles (warp 11 idles)
-    if (lane == 0) {
-      for (int j = 0; j < ntiles; ++j) {
-        const int sb = MULTI ? 0 : (j & 1);
-        ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((MULTI ? j : (j >> 1)) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+    for (int j = 0; j < ntiles; ++j) {
+      const int sb = MULTI ? 0 : (j & 1);
+      ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((MULTI ? j : (j >> 1)) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+      if (ptx::elect_one()) {
         tma_store_3d(&tmap_o, Ps + sb * kQBytes, c0, (tile0 + j) * kQRows, b);
         tma_store_commit();
         tma_store_wait_read();                  // the store has read the buffer: P may be overwritten / the CTA may exit
         ptx::mbar_arrive(&st_done[sb]);
       }
+      __syncwarp();
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, one elected lane issues)
+    {
       const uint32_t idesc_s = ptx::make_idesc_bf16_f32(kQRows, kKeys);                 // A, B K-major
       const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(kQRows, kHD) | (1u << 16);     // B (= V) MN-major
       ptx::mbar_wait(&kv_full, 0u);
@@ -214,11 +221,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::mbar_wait(&q_full[g], static_cast<uint32_t>((j >> 1) & 1));
             ptx::tc_fence_after();
             const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + g * kQBytes));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kHD / 16; ++ks)
-              ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
-            ptx::umma_commit(&s_full[g]);
-            ptx::umma_commit(&q_empty[g]);
+              for (int ks = 0; ks < kHD / 16; ++ks)
+                ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+              ptx::umma_commit(&s_full[g]);
+              ptx::umma_commit(&q_empty[g]);
+            }
+            __syncwarp();
           }
           if (j >= 1) {
             const int jj = j - 1, g = jj & 1;
@@ -226,11 +236,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::mbar_wait(&p_full[g], static_cast<uint32_t>((jj >> 1) & 1));
             ptx::tc_fence_after();
             const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + g * kQBytes));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
-              ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
-                            ks ? 1u : 0u);
-            ptx::umma_commit(&o_full[g]);
+              for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
+                ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
+                              ks ? 1u : 0u);
+              ptx::umma_commit(&o_full[g]);
+            }
+            __syncwarp();
           }
         }
       } else {
@@ -240,14 +253,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           ptx::mbar_wait(&q_full[qb], static_cast<uint32_t>((j >> 1) & 1));
           ptx::tc_fence_after();
           const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + qb * kQBytes));
-          for (int t = 0; t < kt; ++t) {
-            const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + t * kKBytes));
+          if (ptx::elect_one()) {
+            for (int t = 0; t < kt; ++t) {
+              const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + t * kKBytes));
 #pragma unroll
-            for (int ks = 0; ks < kHD / 16; ++ks)
-              ptx::umma_f16(tmem_base + static_cast<uint32_t>(t * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+              for (int ks = 0; ks < kHD / 16; ++ks)
+                ptx::umma_f16(tmem_base + static_cast<uint32_t>(t * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+            }
+            ptx::umma_commit(&s_full[0]);
+            ptx::umma_commit(&q_empty[qb]);
           }
-          ptx::umma_commit(&s_full[0]);
-          ptx::umma_commit(&q_empty[qb]);
+          __syncwarp();
           for (int t = 0; t < kt; ++t) {
             const int pb = t & 1;
             const uint32_t par = (pb ? n_pf[1] : n_pf[0]) & 1u;
@@ -257,12 +273,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             ptx::tc_fence_after();
             const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + pb * kQBytes));
             const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs + t * kKBytes));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kKeys / 16; ++ks)
-              ptx::umma_f16(tmem_o, dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv, (t | ks) ? 1u : 0u);
-            ptx::umma_commit(&p_empty[pb]);
+              for (int ks = 0; ks < kKeys / 16; ++ks)
+                ptx::umma_f16(tmem_o, dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv, (t | ks) ? 1u : 0u);
+              ptx::umma_commit(&p_empty[pb]);
+              if (t == kt - 1) ptx::umma_commit(&o_full[0]);
+            }
+            __syncwarp();
           }
-          ptx::umma_commit(&o_full[0]);
         }
       }
     }
@@ -474,7 +493,8 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");   // one instruction for the whole control warpgroup; 8 * 96 + 4 * 48 = 12 * 80
     if (warp == 8) {
       // ---------------------------------------------------------------- TMA loads
-      if (lane == 0) {
+      // (control warps: the whole warp runs the loop and polls, one elected lane issues — see ptx::elect_one)
+      {
         int prev_bh = -1, n_kv = 0;
         for (int j = 0; j < ntiles; ++j) {
           int bh, qt;
@@ -483,36 +503,43 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           if (bh != prev_bh) {
             const int kb = n_kv & 1;
             if (n_kv >= 2) ptx::mbar_wait(&kv_empty[kb], static_cast<uint32_t>(((n_kv - 2) >> 1) & 1));   // every MMA on the pair two back has retired
-            ptx::mbar_arrive_expect_tx(&kv_full[kb], 2 * kKBytes);
-            tma_load_3d(Ks + kb * kKBytes, &tmap_k, &kv_full[kb], c0, 0, b);
-            tma_load_3d(Vs + kb * kKBytes, &tmap_v, &kv_full[kb], c0, 0, b);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(&kv_full[kb], 2 * kKBytes);
+              tma_load_3d(Ks + kb * kKBytes, &tmap_k, &kv_full[kb], c0, 0, b);
+              tma_load_3d(Vs + kb * kKBytes, &tmap_v, &kv_full[kb], c0, 0, b);
+            }
+            __syncwarp();
             ++n_kv;
             prev_bh = bh;
           }
           const int qb = j & 1;
           if (j >= 2) ptx::mbar_wait(&q_empty[qb], static_cast<uint32_t>(((j - 2) >> 1) & 1));   // the S MMAs of tile j-2 have read this buffer
-          ptx::mbar_arrive_expect_tx(&q_full[qb], kQBytes);
-          tma_load_3d(Qs + qb * kQBytes, &tmap_q, &q_full[qb], c0, qt * kQRows, b);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+            tma_load_3d(Qs + qb * kQBytes, &tmap_q, &q_full[qb], c0, qt * kQRows, b);
+          }
+          __syncwarp();
         }
       }
     } else if (warp == 10) {
       // ---------------------------------------------------------------- TMA stores of the output tiles (warp 11 idles)
-      if (lane == 0) {
-        for (int j = 0; j < ntiles; ++j) {
-          int bh, qt;
-          item(j, bh, qt);
-          const int b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
-          const int sb = j & 1;
-          ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((j >> 1) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+      for (int j = 0; j < ntiles; ++j) {
+        int bh, qt;
+        item(j, bh, qt);
+        const int b = bh / p.heads, c0 = (bh - b * p.heads) * kHD;
+        const int sb = j & 1;
+        ptx::mbar_wait(&o_staged[sb], static_cast<uint32_t>((j >> 1) & 1));   // the rows of O_j are staged in P buffer sb (and fenced)
+        if (ptx::elect_one()) {
           tma_store_3d(&tmap_o, Ps + sb * kQBytes, c0, qt * kQRows, b);
           tma_store_commit();
           tma_store_wait_read();                  // the store has read the buffer: P may be overwritten / the CTA may exit
           ptx::mbar_arrive(&st_done[sb]);
         }
+        __syncwarp();
       }
     } else if (warp == 9) {
-      // ---------------------------------------------------------------- MMA issuer (single thread)
-      if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer (converged warp, one elected lane issues)
+      {
         const uint32_t idesc_s = ptx::make_idesc_bf16_f32(kQRows, kKeys);                 // A, B K-major
         const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(kQRows, kHD) | (1u << 16);     // B (= V) MN-major
         // issue order S_0, S_1, PV_0, S_2, PV_1, ...: the S MMA of the next tile is in flight while a group does its exponentials
@@ -533,11 +560,14 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             ptx::tc_fence_after();
             const uint64_t dq = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Qs + g * kQBytes));
             const uint64_t dk = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ks + kb_s * kKBytes));
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < kHD / 16; ++ks)
-              ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
-            ptx::umma_commit(&s_full[g]);
-            ptx::umma_commit(&q_empty[g]);
+              for (int ks = 0; ks < kHD / 16; ++ks)
+                ptx::umma_f16(tmem_base + static_cast<uint32_t>(g * kKeys), dq + static_cast<uint64_t>(ks * 2), dk + static_cast<uint64_t>(ks * 2), idesc_s, ks ? 1u : 0u);
+              ptx::umma_commit(&s_full[g]);
+              ptx::umma_commit(&q_empty[g]);
+            }
+            __syncwarp();
           }
           if (j >= 1) {
             const int jj = j - 1, g = jj & 1;
@@ -549,15 +579,19 @@ attention_tc_single_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             ptx::tc_fence_after();
             const uint64_t dp = ptx::make_sw128_kmajor_desc(ptx::smem_u32(Ps + g * kQBytes));
             const uint64_t dv = make_sw128_mnmajor_desc(ptx::smem_u32(Vs + kb_pv * kKBytes));
-#pragma unroll
-            for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
-              ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
-                            ks ? 1u : 0u);
-            ptx::umma_commit(&o_full[g]);
             // last tile of its (frame, head): once everything issued so far has retired, the K/V buffer may be refilled
             int bh_next = -1;
             if (j < ntiles) item(j, bh_next, qt_unused);
-            if (j == ntiles || bh_next != bh) ptx::umma_commit(&kv_empty[kb_pv]);
+            const bool last_of_pair = j == ntiles || bh_next != bh;
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < kKeys / 16; ++ks)   // 16 keys per step: +32 B along P's rows, +2 swizzle atoms (2048 B) down V
+                ptx::umma_f16(tmem_o + static_cast<uint32_t>(g * kHD), dp + static_cast<uint64_t>(ks * 2), dv + static_cast<uint64_t>(ks * (2048 >> 4)), idesc_pv,
+                              ks ? 1u : 0u);
+              ptx::umma_commit(&o_full[g]);
+              if (last_of_pair) ptx::umma_commit(&kv_empty[kb_pv]);
+            }
+            __syncwarp();
           }
         }
       }
