@@ -28,6 +28,13 @@
 
 namespace sv {
 
+#ifdef SV_GEMM_TRACE
+__device__ unsigned long long g_trace[4][4096];   // 0 producer (per k-block: slot free), 1 MMA (per k-block: operands landed), 2 MMA per tile (accumulator free), 3 epilogue warp 2 (per tile: 2t = accumulator full, 2t+1 = done)
+#define SV_TRACE(role, idx) do { if (blockIdx.x == 0 && (idx) < 4096) g_trace[role][idx] = clock64(); } while (0)
+#else
+#define SV_TRACE(role, idx) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -118,7 +125,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ------------------------------------------------------------------ TMA producer
     // The whole warp runs the loop in lock step and polls the barriers; one elected lane issues the TMA instructions (see ptx::elect_one).
     {
-      int stage = 0;
+      int stage = 0, tr_kb = 0;
       uint32_t phase = 0;
       // L2 prefetch cursor: runs p.prefetch k-blocks ahead of the load cursor over this CTA's (tile, k-block) sequence
       int pf_tile = first_tile, pf_kb = 0;
@@ -135,6 +142,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           if (p.prefetch > 0) prefetch_next();
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          SV_TRACE(0, tr_kb); ++tr_kb;
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + kATileBytes;
           const bool seg2 = kb >= p.kb_split;   // second A segment (e.g. the adapter tensor next to the MixFFN hidden)
@@ -166,14 +174,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const uint32_t idesc = ptx::make_idesc_bf16_f32(PAIR ? 2 * kBlockM : kBlockM, p.block_n);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
+      int acc = 0, tr_kb = 0, tr_tile = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+        SV_TRACE(2, tr_tile); ++tr_tile;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kAccStride);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
+          SV_TRACE(1, tr_kb); ++tr_kb;
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * stage_bytes);
           const uint64_t da = ptx::make_sw128_kmajor_desc(sa);
@@ -240,6 +250,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int acc = 0;
       uint32_t acc_phase = 0;
       uint32_t n_store = 0;   // stores issued by this warp so far (lane 0's bulk groups)
+      int tr_tile = 0;
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         const int m0 = (tile / p.num_n_tiles) * (PAIR ? 2 * kBlockM : kBlockM) + static_cast<int>(cta_rank) * kBlockM;
         const int n0 = (tile % p.num_n_tiles) * p.block_n;
@@ -254,16 +265,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         __syncwarp();
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (warp == 2) SV_TRACE(3, 16 * tr_tile);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
         uint32_t r_a[32], r_b[32];
         if (half < nchunks) ptx::tmem_ld_x32(t_row + static_cast<uint32_t>(half * 32), r_a);
         auto emit = [&](const uint32_t (&r)[32], int c) {
           uint8_t* sb = sbase + (n_store % nb) * kEpiBufBytes;
+          if (warp == 2) SV_TRACE(3, 16 * tr_tile + 1 + 3 * (c >> 1));
           if (n_store >= nb) {   // the store issued from this buffer nb chunks ago has finished reading it
             if (ptx::elect_one()) ptx::bulk_wait_group_read(static_cast<int>(nb) - 1);
             __syncwarp();
           }
+          if (warp == 2) SV_TRACE(3, 16 * tr_tile + 2 + 3 * (c >> 1));
           uint32_t w[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -293,6 +307,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (warp == 2) SV_TRACE(3, 16 * tr_tile + 3 + 3 * (c >> 1));
           ++n_store;
         };
         for (int c = half; c < nchunks; c += 4) {
@@ -310,6 +325,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (PAIR) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));   // the leader's MMA warp owns both TMEMs
           else ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (warp == 2) SV_TRACE(3, 16 * tr_tile + 15);
+        ++tr_tile;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -337,6 +354,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t acc_phase = 0;
       uint32_t n_chunk = 0;    // chunks this warp has processed so far: buffer = n_chunk % nb, barrier parity = (n_chunk / nb) & 1
       uint32_t n_loaded = 0;   // residual loads issued so far (same numbering)
+      int tr_tile = 0;
       const int x = (lane >> 1) & 3;   // 64B swizzle: 16-byte piece j of row r lives at r*64 + ((j ^ ((r >> 1) & 3)) << 4)
       const int m_step = PAIR ? 2 * kBlockM : kBlockM;
       auto chunks_of = [&](int n0) {   // this warp takes the 16-column chunks half, half + 2, ... of a tile
@@ -379,6 +397,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         __syncwarp();
         ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (warp == 2) SV_TRACE(3, 16 * tr_tile);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * kAccStride) + (static_cast<uint32_t>(quarter * 32) << 16);
         uint32_t r_a[16], r_b[16];
@@ -441,6 +460,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (PAIR) ptx::mbar_arrive_cluster(ptx::map_to_cta(ptx::smem_u32(&tmem_empty_bar[acc]), 0u));
           else ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (warp == 2) SV_TRACE(3, 16 * tr_tile + 15);
+        ++tr_tile;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -622,17 +643,20 @@ int gemm_plan(const GemmDesc& d, GemmPlan* plan) {
   p.tma_out = ((d.out_fp32 || d.residual == nullptr) && tma_out_env) ? 1 : 0;
   if (p.tma_out && d.out_fp32 && ((d.ldc * 4) % 16 != 0 || (d.residual && (d.ldr * 4) % 16 != 0))) p.tma_out = 0;
   p.block_n = gemm_pick_block_n(d.M, d.N, d.K, sms, (p.tma_out && !d.out_fp32) ? 32 : 16);
-  // CTA-pair mode (cta_group::2): each CTA stages half of the B tile, so the ring holds more k-blocks per byte of shared memory.
-  // Measured on B200 (profiles/r02/gemm_elect.log, after the MMA issue moved to a converged warp + elect.sync): it wins where the
-  // k-loop dominates — K = 1280..8192: 184 -> 172 us (156 800 x 320 x 1360 + residual), 1015 -> 902 us (39 200 x 2048 x 8192 =
-  // 1.46 PFLOP/s), 247 -> 224 us (K = 2176) — and loses 15-35 % on the K <= 320 GEMMs, whose time is the epilogue's (two CTAs'
-  // epilogues gate every accumulator hand-back).  'auto' (-1) therefore enables it for K >= 1024 when there are enough 256-row tiles
-  // to fill the machine; GemmDesc::pair / SURGVID_GEMM_PAIR force it on (1) or off (0).
+  // CTA-pair mode (cta_group::2): each CTA stages half of the B tile, so the ring holds more k-blocks per byte of shared memory
+  // and the L2 -> shared-memory traffic of the weights halves.  Measured on B200 (profiles/r02/gemm_pair_relaxed_arrive.log, after
+  // (1) the MMA issue moved to a converged warp + elect.sync and (2) the accumulator hand-back stopped using a .release.cluster
+  // arrive, which had cost every epilogue warp ~1 800 cycles per tile): 143.7 -> 129.1 us (156 800 x 1280 x 320), 185 -> 173 us
+  // (x 320 x 1360 + residual), 1 025 -> 912 us (39 200 x 2048 x 8192 = 1.44 PFLOP/s), 228 -> 197 us (112 700 x 2048 x 512); a tie
+  // (+-2 %) on the fp32 read-modify-write GEMMs with K <= 320, whose time is the residual stream's.  'auto' (-1) enables it when
+  // there are enough 256-row tiles to fill the machine and either K >= 512 or the result is bf16 with N >= 320;
+  // GemmDesc::pair / SURGVID_GEMM_PAIR force it on (1) or off (0).  Results are bit-identical to single-CTA tiles.
   {
     static const int pair_env = getenv("SURGVID_GEMM_PAIR") ? atoi(getenv("SURGVID_GEMM_PAIR")) : -1;
     const int want = d.pair >= 0 ? d.pair : pair_env;
     const long long pair_tiles = static_cast<long long>(ceil_div(d.M, 2 * kBlockM)) * ceil_div(d.N, p.block_n);
-    p.pair = want >= 0 ? (want > 0 ? 1 : 0) : ((d.K >= 1024 && pair_tiles >= sms / 2) ? 1 : 0);
+    const bool pays = d.K >= 512 || (!d.out_fp32 && d.N >= 320);
+    p.pair = want >= 0 ? (want > 0 ? 1 : 0) : ((pays && pair_tiles >= sms / 2) ? 1 : 0);
   }
   if (p.pair && (p.block_n % 32 != 0)) p.block_n = round_up(p.block_n, 32);  // each CTA stages block_n/2 rows of B (multiple of 16)
   if (p.block_n > 256) { p.block_n = 256; }
@@ -743,6 +767,10 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
 }
 
 }  // namespace sv
+
+#ifdef SV_GEMM_TRACE
+extern "C" int sv_debug_gemm_trace(void* host_out) { return cudaMemcpyFromSymbol(host_out, sv::g_trace, sizeof(sv::g_trace)) == cudaSuccess ? 0 : 1; }
+#endif
 
 extern "C" int sv_op_gemm_bf16(const uint16_t* A, int64_t lda, const uint16_t* W, int64_t ldw, int32_t M, int32_t N, int32_t K,
                                const float* bias, int32_t act, const float* residual, int64_t ldr, void* out, int64_t ldc,

@@ -166,8 +166,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta_
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
   return r;
 }
+// Arrive on a (possibly remote) CTA's barrier.  Default semantics (.release at CTA scope) on purpose: a .release.cluster arrive
+// makes the thread wait until all of its earlier writes are visible cluster-wide — measured ~1 800 cycles per call in the GEMM
+// epilogue (profiles/r02/gemm_trace_cta0.log) — and the only ordering the accumulator hand-back needs is the tcgen05 one, which
+// tcgen05.fence::before_thread_sync in front of the arrive provides.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // In a CTA pair the transaction bytes of BOTH CTAs' loads are counted on the leader (rank 0) CTA's barrier: clearing the
 // CTA-rank bit of the shared::cluster address of our own barrier names the leader's copy.
