@@ -282,14 +282,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + i);
-            float v0 = __uint_as_float(r[i]) + b4.x, v1 = __uint_as_float(r[i + 1]) + b4.y, v2 = __uint_as_float(r[i + 2]) + b4.z,
-                  v3 = __uint_as_float(r[i + 3]) + b4.w;
-            if constexpr (ACT == ACT_GELU) {
-              f32x2 lo = f2_pack(v0, v1), hi = f2_pack(v2, v3);
-              f2_gelu_erf_poly_x2(lo, hi);
-              f2_unpack(lo, v0, v1);
-              f2_unpack(hi, v2, v3);
-            } else if constexpr (ACT == ACT_RELU) {
+            // packed adds (one FADD2 per two columns: the epilogue shares four issue ports with seven other warps)
+            f32x2 lo = f2_add(f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), f2_pack(b4.x, b4.y));
+            f32x2 hi = f2_add(f2_pack(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), f2_pack(b4.z, b4.w));
+            if constexpr (ACT == ACT_GELU) f2_gelu_erf_poly_x2(lo, hi);
+            float v0, v1, v2, v3;
+            f2_unpack(lo, v0, v1);
+            f2_unpack(hi, v2, v3);
+            if constexpr (ACT == ACT_RELU) {
               v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
             }
             w[i >> 1] = pack_bf16x2(v0, v1);
@@ -419,17 +419,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int j = 0; j < 4; ++j) {
             float4* pp = reinterpret_cast<float4*>(rowp + ((j ^ x) << 2));
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c16 * 16 + j * 4);
-            float4 v = make_float4(__uint_as_float(r[4 * j]) + b4.x, __uint_as_float(r[4 * j + 1]) + b4.y, __uint_as_float(r[4 * j + 2]) + b4.z,
-                                   __uint_as_float(r[4 * j + 3]) + b4.w);
-            if constexpr (ACT == ACT_GELU) {
-              v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-            } else if constexpr (ACT == ACT_RELU) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            f32x2 lo = f2_add(f2_pack(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), f2_pack(b4.x, b4.y));       // packed adds: half
+            f32x2 hi = f2_add(f2_pack(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), f2_pack(b4.z, b4.w));   // the issue slots
+            if constexpr (ACT != ACT_NONE) {
+              float4 a;
+              f2_unpack(lo, a.x, a.y);
+              f2_unpack(hi, a.z, a.w);
+              if constexpr (ACT == ACT_GELU) {
+                a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+              } else {
+                a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+              }
+              lo = f2_pack(a.x, a.y);
+              hi = f2_pack(a.z, a.w);
             }
             if constexpr (RESID) {
               const float4 q = *pp;
-              v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+              lo = f2_add(lo, f2_pack(q.x, q.y));
+              hi = f2_add(hi, f2_pack(q.z, q.w));
             }
+            float4 v;
+            f2_unpack(lo, v.x, v.y);
+            f2_unpack(hi, v.z, v.w);
             *pp = v;
           }
           ptx::fence_proxy_async_smem();
