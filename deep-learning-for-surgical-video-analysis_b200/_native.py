@@ -13,7 +13,8 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_si
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libsurgvid.so")
+# SURGVID_LIB: load another build of the same native library (same-box A/B of two builds); never a non-native path
+LIB_PATH = os.environ.get("SURGVID_LIB") or os.path.join(_PKG_DIR, "lib", "libsurgvid.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_DIR), "include")
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "dwconv_tma.cu", "stem.cu", "mixffn.cu", "mstcn.cu", "trans_head.cu", "evp.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
