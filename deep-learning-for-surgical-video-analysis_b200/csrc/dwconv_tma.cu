@@ -37,7 +37,6 @@ struct DwParams {
   long long ldo;
   int tiles_x, tiles_y, cblks;
   int tw;  // output columns per tile actually used (<= kTW); box width = tw + 2
-  int order;             // 0: channel block outermost, contiguous tile range per CTA (round 1); 1: channel block fastest, round-robin
   int stages, prefetch;  // shared-memory ring depth (<= kMaxStages) and tiles requested ahead of the one being computed
   int num_tiles;
   int tiles_per_cblk;
@@ -77,12 +76,8 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   // producer, issuing the load of tile k+kPrefetch at the top of iteration k.  (A dedicated producer warp would make
   // 9 warps per CTA = 5 on one scheduler at 2 CTAs/SM, capping the kernel at 96 registers; the consumer loop wants more.)
   auto issue_tile = [&](int t, int stage, uint32_t phase) {
-    // tile order (round 2, p.order == 1): channel block FASTEST and tiles dealt round-robin to the CTAs, so that the CTAs running at the
-    // same time read / write all channel blocks of the same pixels — whole 2*C-byte pixel rows per DRAM page instead of one 256-byte
-    // slice of every row (with the channel block outermost the achieved bandwidth fell with C: 3.9 / 3.3 / 3.0 / 2.9 TB/s at C = 256 /
-    // 512 / 1280 / 2048)
-    const int cblk = p.order ? t % p.cblks : t / p.tiles_per_cblk;
-    int r = p.order ? t / p.cblks : t - cblk * p.tiles_per_cblk;
+    const int cblk = t / p.tiles_per_cblk;
+    int r = t - cblk * p.tiles_per_cblk;
     const int per_b = p.tiles_y * p.tiles_x;
     const int b = r / per_b;
     r -= b * per_b;
@@ -95,21 +90,17 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   // each CTA walks one contiguous range of tiles: neighbouring tiles (shared halos) are loaded back to back and the
   // 128-channel weight block in registers changes at most a couple of times per CTA
   const int per_cta = p.num_tiles / static_cast<int>(gridDim.x), extra = p.num_tiles % static_cast<int>(gridDim.x);
-  // order 0: a contiguous range [t_begin, t_end) of tiles per CTA; order 1: tiles blockIdx.x, blockIdx.x + gridDim.x, ... (the loops below
-  // run over the CTA-local index k and map it to a tile with tile_of)
-  const int n_local = per_cta + (static_cast<int>(blockIdx.x) < extra ? 1 : 0);
-  const int t_first = p.order ? static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x) * per_cta + min(static_cast<int>(blockIdx.x), extra);
-  const int t_stride = p.order ? static_cast<int>(gridDim.x) : 1;
-  const int t_begin = 0, t_end = n_local;
-  auto tile_of = [&](int k) { return t_first + k * t_stride; };
-  // (A converged warp 0 with an elected lane issuing — the pattern that pays in the GEMM and attention control warps — was measured 4 %
-  // SLOWER here, same box: 23.6 -> 24.6 ms per step: warp 0 is also a consumer and all of its lanes then run the tile decode.)
+  const int t_begin = static_cast<int>(blockIdx.x) * per_cta + min(static_cast<int>(blockIdx.x), extra);
+  const int t_end = t_begin + per_cta + (static_cast<int>(blockIdx.x) < extra ? 1 : 0);
+  // Measured and NOT adopted (round 2, profiles/r02/order_ab_negative.log): a run-time tile order with the channel block fastest and tiles
+  // dealt round-robin (slower: weight reloads, lost halo reuse), and warp 0 as a converged producer with an elect.sync lane (no gain:
+  // one TMA per 7 x 8 x 128 outputs is not where this arithmetic-bound kernel spends its time).
   const bool is_producer = threadIdx.x == 0;
   int pt = t_begin, pstage = 0;  // producer cursor
   uint32_t pphase = 0;
   if (is_producer) {
     for (int i = 0; i < p.prefetch && pt < t_end; ++i, ++pt) {
-      issue_tile(tile_of(pt), pstage, pphase);
+      issue_tile(pt, pstage, pphase);
       if (++pstage == p.stages) { pstage = 0; pphase ^= 1u; }
     }
   }
@@ -125,7 +116,7 @@ dwconv3x3_gelu_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const DwPa
   for (int q = 0; q < NP; ++q) biasv[q] = 0;
   for (int t = t_begin; t < t_end; ++t) {
     if (is_producer && pt < t_end) {
-      issue_tile(tile_of(pt), pstage, pphase);
+      issue_tile(pt, pstage, pphase);
       ++pt;
       if (++pstage == p.stages) { pstage = 0; pphase ^= 1u; }
     }
@@ -287,8 +278,6 @@ int dwconv_tma_launch(const DwconvPlan& plan, cudaStream_t st) {
   p.w9c = plan.w9c; p.bias = plan.bias; p.out = plan.out; p.B = plan.B; p.H = plan.H; p.W = plan.W; p.C = plan.C; p.ldo = plan.ldo;
   p.tw = plan.tw;
   p.stages = stages; p.prefetch = prefetch;
-  static const int env_order = [] { const char* e = getenv("SURGVID_DW_ORDER"); return e ? atoi(e) : 0; }();
-  p.order = env_order ? 1 : 0;
   p.tiles_x = ceil_div(plan.W, plan.tw); p.tiles_y = ceil_div(plan.H, kTH); p.cblks = plan.C / cb;
   const long long nt = static_cast<long long>(p.cblks) * plan.B * p.tiles_y * p.tiles_x;
   if (nt >= (1LL << 31)) return fail(SV_ERR_INVALID, "dwconv: more than 2^31 tiles");

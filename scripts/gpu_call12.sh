@@ -3,10 +3,10 @@
 mkdir -p gpurun_out/r02
 {
 for o in 0 1; do
-  echo "== DW_ORDER=$o ATTN_ORDER=$o B=200"; SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py dwconv
-  SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py attn
-  echo "== DW_ORDER=$o ATTN_ORDER=$o B=1159"; SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py dwconv
-  SURGVID_DW_ORDER=$o SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py attn
+  echo "== DW_ORDER=$o ATTN_ORDER=$o B=200"; SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py dwconv
+  SURGVID_ATTN_ORDER=$o REPS=20 python scripts/op_bench.py attn
+  echo "== DW_ORDER=$o ATTN_ORDER=$o B=1159"; SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py dwconv
+  SURGVID_ATTN_ORDER=$o B=1159 REPS=10 python scripts/op_bench.py attn
 done
 } > gpurun_out/r02/order_ab.txt 2>&1
 timeout 600 python -m pytest tests/test_kernels_gpu.py -x -q -m gpu -k "dwconv or attention" > gpurun_out/r02/order_tests.txt 2>&1; echo "tests rc=$?"
