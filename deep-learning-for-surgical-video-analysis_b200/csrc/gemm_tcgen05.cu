@@ -806,6 +806,7 @@ extern "C" int sv_op_gemm_bf16_cat(const uint16_t* A, int64_t lda, const uint16_
   d.W = reinterpret_cast<const sv::bf16*>(W); d.ldw = ldw;
   d.M = M; d.N = N; d.K = K; d.bias = bias; d.act = act; d.residual = residual; d.ldr = ldr;
   d.out = out; d.ldc = ldc; d.out_fp32 = out_fp32;
+  if (const char* e = getenv("SURGVID_GEMM_PAIR")) d.pair = atoi(e);  // test hook, as in sv_op_gemm_bf16
   sv::GemmPlan plan;
   SV_TRY(sv::gemm_plan(d, &plan));
   return sv::gemm_launch(plan, static_cast<cudaStream_t>(stream));

@@ -223,6 +223,30 @@ def test_gemm_cta_pair_mode(M, N, K, monkeypatch):
     assert (pair_bf16.float() - ref2).abs().max().item() < 3e-2 * max(1.0, ref2.abs().max().item())
 
 
+@pytest.mark.parametrize("M,N,K1,K2", [(39200, 320, 1280, 80), (1000, 128, 512, 32), (70000, 64, 256, 16)])
+def test_gemm_cat_cta_pair_mode(M, N, K1, K2, monkeypatch):
+    """The fc2 form the model launches in CTA-pair mode: A given as two K segments, fp32 result accumulated IN PLACE into the residual
+    stream.  Pair mode (forced on, and as the plan selects it by itself) must agree with single-CTA tiles bit for bit."""
+    a = _rand((M, K1), 111, dtype=torch.bfloat16)
+    a2 = _rand((M, K2), 112, dtype=torch.bfloat16)
+    w = _rand((N, K1 + K2), 113, 1.0 / math.sqrt(K1 + K2), dtype=torch.bfloat16)
+    bias = _rand((N,), 114, 0.5)
+    x0 = _rand((M, N), 115)
+    outs = {}
+    for mode in ("0", "1", None):
+        if mode is None:
+            monkeypatch.delenv("SURGVID_GEMM_PAIR", raising=False)
+        else:
+            monkeypatch.setenv("SURGVID_GEMM_PAIR", mode)
+        x = x0.clone()
+        ops.gemm_bf16_cat(a, a2, w, bias=bias, residual=x, out=x)
+        outs[mode] = x
+    torch.cuda.synchronize()
+    ref = torch.cat([a, a2], 1).float() @ w.float().t() + bias + x0
+    assert (outs["1"] - ref).abs().max().item() < 3e-3 * max(1.0, ref.abs().max().item())
+    assert torch.equal(outs["1"], outs["0"]) and torch.equal(outs[None], outs["0"])
+
+
 @pytest.mark.parametrize("cfg", [
     # (frames, H, W, hidden, N, tail_cols): the three fusable stages of mit_b3_evp at 224^2, a no-tail case, ragged row tiles,
     # and enough frames that every CTA of the persistent grid walks several tiles
