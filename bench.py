@@ -47,6 +47,19 @@ FLOPS_PER_FRAME_REF = 16.664e9  # reference graph @224^2 with flow (SURVEY.md §
 FLOPS_PER_FRAME_REF_480 = 166.02e9  # @480x854
 
 
+
+def gemm_kernel_sha256(root):
+    """sha256 of the GEMM's device + plan code (gemm_tcgen05.cu up to the extern "C" op wrappers, gemm.cuh, gemm_epi.cuh, ptx.cuh):
+    recorded next to the ncu-measured traffic so that a bench run can tell whether that capture still describes the kernel it runs."""
+    import hashlib, os
+    d = os.path.join(root, "deep-learning-for-surgical-video-analysis_b200", "csrc")
+    h = hashlib.sha256()
+    src = open(os.path.join(d, "gemm_tcgen05.cu")).read()
+    h.update(src.split('extern "C"')[0].encode())
+    for f in ("gemm.cuh", "gemm_epi.cuh", "ptx.cuh"):
+        h.update(open(os.path.join(d, f)).read().encode())
+    return h.hexdigest()
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -359,7 +372,7 @@ class Ctx:
                            "alg_mbytes_per_frame": by_k[i] / T / 1e6, "hbm_gbs": gbs, "hbm_frac": (gbs / peaks["hbm_gbs"] if gbs else None)}
         tflops = fl.value / (ms_k[0] / 1e3) / 1e12 if ms_k[0] else 0.0
         gbs = by_k[0] / (ms_k[0] / 1e3) / 1e9 if ms_k[0] else 0.0
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_current = None, None, None
         for rd in ("r02", "r01"):
             tpath = os.path.join(ROOT, "profiles", rd, "gemm_traffic.json")
             if os.path.exists(tpath) and (args_hw(self.args) == (224, 224)):
@@ -371,11 +384,14 @@ class Ctx:
                 else:
                     traffic = tj.get("traffic_bytes_per_launch")
                 traffic_src = tj.get("source")
+                traffic_current = (tj.get("gemm_kernel_sha256") == gemm_kernel_sha256(ROOT)) if tj.get("gemm_kernel_sha256") else None
                 break
         # The dominant kernel is the tcgen05 GEMM.  Its launches have an aggregate arithmetic intensity of ~130 FLOP/B (K = 64..320 for most
         # of them) against a ridge of ~213 FLOP/B, so the BINDING roofline is HBM; the tensor-pipe figures are reported alongside.
         roofline = {"bound": "hbm", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                    # True: the GEMM device + plan code of this tree is byte-identical to the one the ncu capture was taken with
+                    "traffic_capture_matches_kernel": traffic_current,
                     "peak_source": peaks["source"] + " (copy bandwidth)",
                     "avg_launch_ms": ms_k[0] / max(1, n_k[0]), "launches_profiled": int(n_k[0]), "frames_profiled": T,
                     "algorithmic_bytes_per_launch": by_k[0] / max(1, n_k[0]), "algorithmic_bytes_per_frame": by_k[0] / T,

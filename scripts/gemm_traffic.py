@@ -1,7 +1,20 @@
 """Derive per-launch DRAM traffic and per-class duration shares from an ncu launch list
 (`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv`).
 usage: python scripts/gemm_traffic.py <launches.csv> [out.json] [source note]"""
-import collections, csv, json, sys
+import collections, csv, json, os, sys
+
+def gemm_kernel_sha256(root):
+    """sha256 of the GEMM's device + plan code (gemm_tcgen05.cu up to the extern "C" op wrappers, gemm.cuh, gemm_epi.cuh, ptx.cuh):
+    recorded next to the ncu-measured traffic so that a bench run can tell whether that capture still describes the kernel it runs."""
+    import hashlib, os
+    d = os.path.join(root, "deep-learning-for-surgical-video-analysis_b200", "csrc")
+    h = hashlib.sha256()
+    src = open(os.path.join(d, "gemm_tcgen05.cu")).read()
+    h.update(src.split('extern "C"')[0].encode())
+    for f in ("gemm.cuh", "gemm_epi.cuh", "ptx.cuh"):
+        h.update(open(os.path.join(d, f)).read().encode())
+    return h.hexdigest()
+
 
 path = sys.argv[1]
 rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) >= 15 and r[0].isdigit()]
@@ -34,6 +47,7 @@ if g and len(sys.argv) > 2:
     out = {"kernel": "gemm_bf16_tcgen05_kernel", "traffic_bytes_per_launch": int((g["rd"] + g["wr"]) / g["launches"]), "launches": g["launches"],
            "frames_profiled": frames, "traffic_bytes_per_frame": (g["rd"] + g["wr"]) / frames,
            "dram_bytes_read": g["rd"], "dram_bytes_write": g["wr"], "source": sys.argv[3] if len(sys.argv) > 3 else path,
-           "class_time_shares_under_ncu": {k: round(c["time"] / tot, 4) for k, c in cls.items()}}
+           "class_time_shares_under_ncu": {k: round(c["time"] / tot, 4) for k, c in cls.items()},
+           "gemm_kernel_sha256": gemm_kernel_sha256(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))}
     json.dump(out, open(sys.argv[2], "w"), indent=1)
     print("wrote", sys.argv[2], out["traffic_bytes_per_launch"])
